@@ -1,0 +1,104 @@
+"""tcgen05 GEMM vs a plain torch fp32 matmul of the same bf16-rounded operands (all operand majors / epilogues)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(rows, cols, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _ref(A, B, a_mn, b_mn):
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float().t() if b_mn else B.float()
+    return Af @ Bf.t()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 768), (387, 2304, 768), (1000, 768, 3072),
+                                   (258, 136, 200), (129 * 6, 768, 768), (64, 171, 2304)])
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    from editor_b200 import lib
+    Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    Kp = (K + 7) // 8 * 8
+    A = _mk(K, Mp, 1)[:, :M] if a_mn else _mk(M, Kp, 1)[:, :K]
+    B = _mk(K, Np, 2)[:, :N] if b_mn else _mk(N, Kp, 2)[:, :K]
+    D = torch.full((M, Np), 7.0, dtype=torch.float32, device="cuda")
+    lib.gemm(A, B, D, M, N, K, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, a_mn, b_mn)
+    err = (D[:, :N] - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
+    if Np > N:
+        assert torch.all(D[:, N:] == 7.0)  # padding columns untouched
+
+
+def test_gemm_bias_gelu_bf16_out():
+    from editor_b200 import lib
+    M, N, K = 516, 3072, 768
+    A, B = _mk(M, K, 3, 0.5), _mk(N, K, 4, 0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    lib.gemm(A, B, D, M, N, K, epilogue=lib.EPI_GELU, bias=bias, out2=pre)
+    torch.cuda.synchronize()
+    ref_pre = A.float() @ B.float().t() + bias
+    ref = torch.nn.functional.gelu(ref_pre)
+    assert (pre.float() - ref_pre).abs().max().item() < 2e-2
+    assert (D.float() - ref).abs().max().item() < 2e-2
+
+
+def test_gemm_residual_inplace():
+    from editor_b200 import lib
+    M, N, K = 774, 768, 3072
+    A, B = _mk(M, K, 5, 0.5), _mk(N, K, 6, 0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    x = torch.randn(M, N, device="cuda")
+    ref = x + A.float() @ B.float().t() + bias
+    lib.gemm(A, B, x, M, N, K, epilogue=lib.EPI_RESIDUAL, bias=bias, aux=x)
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_gemm_gelu_bwd_and_splitk():
+    from editor_b200 import lib
+    M, N, K = 640, 3072, 768
+    dY, W = _mk(M, K, 7, 0.5), _mk(K, N, 8, 0.05)           # dH = dY @ W  (W stored [K_in=768 rows(k), N cols])
+    pre = _mk(M, N, 9)
+    D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    lib.gemm(dY, W, D, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=pre)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(dY.float() @ W.float())
+    torch.cuda.synchronize()
+    assert (D.float() - x.grad).abs().max().item() < 3e-2
+    # wgrad with split-K: dW[N', K'] = dY^T X, reduction over M rows
+    Mr, Nw, Kw = 129 * 48, 768, 768
+    dY2, X2 = _mk(Mr, Nw, 10, 0.1), _mk(Mr, Kw, 11, 0.1)
+    dW = torch.zeros(Nw, Kw, dtype=torch.float32, device="cuda")
+    lib.gemm(dY2, X2, dW, Nw, Kw, Mr, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=8)
+    torch.cuda.synchronize()
+    ref = dY2.float().t() @ X2.float()
+    assert (dW - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_gemm_throughput_report(capsys):
+    """Not an assertion on speed: prints TFLOP/s of the fc1-shaped GEMM for the log."""
+    from editor_b200 import lib
+    M, N, K = 49536, 3072, 768
+    A, B = _mk(M, K, 12, 0.5), _mk(N, K, 13, 0.05)
+    D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    for _ in range(3):
+        lib.gemm(A, B, D, M, N, K)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        lib.gemm(A, B, D, M, N, K)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    with capsys.disabled():
+        print("\n[gemm 49536x3072x768 bf16] %.3f ms  %.1f TFLOP/s" % (ms, 2.0 * M * N * K / ms / 1e9))
+    ref = A[:256].float() @ B.float().t()
+    assert (D[:256].float() - ref).abs().max().item() < 5e-2
