@@ -1,0 +1,1 @@
+"""editor_b200 -- B200-native (sm_100a) implementation of the EDITOR hot path behind the reference's model API."""

@@ -21,4 +21,89 @@ int edb_gemm_bf16(const EdbGemmDesc* d, void* stream) {
     return edb::gemm_bf16(*d, static_cast<cudaStream_t>(stream));
 }
 
+#define ST static_cast<cudaStream_t>(stream)
+
+int edb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
+                      long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, void* stream) {
+    return edb::layernorm_fwd(x, ldx, gamma, beta, eps, y, ldy, y_f32, mean, rstd, rows, dim, ST);
+}
+size_t edb_layernorm_bwd_workspace_bytes(void) { return edb::layernorm_bwd_workspace_bytes(); }
+int edb_layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
+                      const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg,
+                      void* g_bf16, long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace,
+                      size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, void* stream) {
+    return edb::layernorm_bwd(dy, lddy, dy_f32, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, g_bf16, ldgb, dgamma, dbeta,
+                              dcol, workspace, ws_bytes, rows, dim, row_scale, scale_group, ST);
+}
+int edb_colsum(const void* src, long long ld, int src_f32, int rows, int n, float* out, void* stream) {
+    return edb::colsum(src, ld, src_f32, rows, n, out, ST);
+}
+int edb_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream) { return edb::cast_f32_bf16(src, dst, n, ST); }
+int edb_split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, void* stream) {
+    return edb::split_bf16x3(src, ld, rows, K, dst, role, ST);
+}
+int edb_patch_im2col(const float* rgb, const float* ni, const float* ti, int B, int H, int W, void* out, long long ldo,
+                     int out_f32, void* stream) {
+    return edb::patch_im2col(rgb, ni, ti, B, H, W, out, ldo, out_f32, ST);
+}
+int edb_embed_assemble(const float* patch_out, const float* cls, const float* pos, const float* sie,
+                       const long long* cam, float coe, int S, int B, int P, float* x, void* stream) {
+    return edb::embed_assemble(patch_out, cls, pos, sie, cam, coe, S, B, P, x, ST);
+}
+int edb_embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos,
+                           float* dsie, void* dpatch_bf16, void* stream) {
+    return edb::embed_assemble_bwd(g, S, B, P, cam, coe, dpos, dsie, dpatch_bf16, ST);
+}
+static bool tc_eligible(const EdbAttnDesc* d) {
+    return d->impl == 0 && !d->f32 && d->seq_off == nullptr && d->fixed_len == 129 && d->heads == 12 && d->P != nullptr &&
+           d->p_rows == 129 && d->ldp == 136;
+}
+int edb_attention_fwd(const EdbAttnDesc* d, void* stream) {
+    if (d == nullptr) return edb::edb_set_error(EDB_ERR_SHAPE, "null descriptor");
+    if (tc_eligible(d)) return edb::attention_tc_fwd(*d, ST);
+    return edb::attention_simple(*d, false, ST);
+}
+int edb_attention_bwd(const EdbAttnDesc* d, void* stream) {
+    if (d == nullptr) return edb::edb_set_error(EDB_ERR_SHAPE, "null descriptor");
+    if (tc_eligible(d)) return edb::attention_tc_bwd(*d, ST);
+    return edb::attention_simple(*d, true, ST);
+}
+int edb_freq_counts(const float* rgb, const float* ni, const float* ti, int B, int H, int W, int* counts, void* stream) {
+    return edb::freq_counts(rgb, ni, ti, B, H, W, counts, ST);
+}
+int edb_topk_mask(const void* vals, int vals_f32, long long ld, int rows, int n, int k, unsigned* mask, int accumulate,
+                  void* stream) {
+    return edb::topk_mask(vals, vals_f32, ld, rows, n, k, mask, accumulate, ST);
+}
+int edb_rollout_topk(const void* const* maps_host, int layers, int maps_f32, int nseq, int B, int heads,
+                     long long p_rows, long long ldp, int k, unsigned* index, unsigned* mod_mask, float* rows_out,
+                     void* stream) {
+    return edb::rollout_topk(maps_host, layers, maps_f32, nseq, B, heads, p_rows, ldp, k, index, mod_mask, rows_out, ST);
+}
+int edb_index_finalize(const unsigned* index, int B, int* seq_off, int* seq_off3, void* stream) {
+    return edb::index_finalize(index, B, seq_off, seq_off3, ST);
+}
+int edb_sfts_pack_fwd(const float* tokens, const unsigned* index, const int* seq_off, int B, long long cap,
+                      float* packed, float* loss_bcc, void* stream) {
+    return edb::sfts_pack_fwd(tokens, index, seq_off, B, cap, packed, loss_bcc, ST);
+}
+int edb_sfts_pack_bwd(const float* tokens, const unsigned* index, const int* seq_off, int B, long long cap,
+                      const float* d_packed, const float* g_loss, float* d_tokens, void* stream) {
+    return edb::sfts_pack_bwd(tokens, index, seq_off, B, cap, d_packed, g_loss, d_tokens, ST);
+}
+int edb_joint_gather(float* mod, long long cap, float* joint, const int* seq_off, int B, int max_len, int dir,
+                     void* stream) {
+    return edb::joint_gather(mod, cap, joint, seq_off, B, max_len, dir, ST);
+}
+int edb_pool_fwd(const float* x, const int* seq_off, int B, float* cls_out, float* patch_mean, int* num, void* stream) {
+    return edb::pool_fwd(x, seq_off, B, cls_out, patch_mean, num, ST);
+}
+int edb_pool_bwd(const float* d_cls, const float* d_patch, const int* seq_off, const int* num, int B, int max_len,
+                 float* dx, void* stream) {
+    return edb::pool_bwd(d_cls, d_patch, seq_off, num, B, max_len, dx, ST);
+}
+int edb_cls_rows(float* packed, long long cap, const int* seq_off, int B, float* rows, int dir, void* stream) {
+    return edb::cls_rows(packed, cap, seq_off, B, rows, dir, ST);
+}
+
 }  // extern "C"

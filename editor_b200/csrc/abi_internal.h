@@ -26,4 +26,39 @@ int num_sms();
 int make_tmap_bf16(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_rows);
 int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream);
 
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
+                  long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, cudaStream_t st);
+size_t layernorm_bwd_workspace_bytes();
+int layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
+                  const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg, void* g_bf16,
+                  long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace, size_t ws_bytes, int rows,
+                  int dim, const float* row_scale, int scale_group, cudaStream_t st);
+int colsum(const void* src, long long ld, int src_f32, int rows, int N, float* out, cudaStream_t st);
+int cast_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
+int split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, cudaStream_t st);
+int patch_im2col(const float* rgb, const float* ni, const float* ti, int B, int H, int W, void* out, long long ldo,
+                 int out_f32, cudaStream_t st);
+int embed_assemble(const float* patch_out, const float* cls, const float* pos, const float* sie, const long long* cam,
+                   float coe, int S, int B, int P, float* x, cudaStream_t st);
+int embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos, float* dsie,
+                       void* dpatch_bf16, cudaStream_t st);
+int attention_simple(const EdbAttnDesc& d, bool bwd, cudaStream_t st);
+int attention_tc_fwd(const EdbAttnDesc& d, cudaStream_t st);
+int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st);
+int freq_counts(const float* rgb, const float* ni, const float* ti, int B, int H, int W, int* counts, cudaStream_t st);
+int topk_mask(const void* vals, int vals_f32, long long ld, int rows, int n, int k, unsigned* mask, int accumulate,
+              cudaStream_t st);
+int rollout_topk(const void* const* maps, int layers, int maps_f32, int nseq, int B, int heads, long long p_rows,
+                 long long ldp, int k, unsigned* index, unsigned* mod_mask, float* rows_out, cudaStream_t st);
+int index_finalize(const unsigned* index, int B, int* seq_off, int* seq_off3, cudaStream_t st);
+int sfts_pack_fwd(const float* tokens, const unsigned* index, const int* seq_off, int B, long long cap, float* packed,
+                  float* loss_bcc, cudaStream_t st);
+int sfts_pack_bwd(const float* tokens, const unsigned* index, const int* seq_off, int B, long long cap,
+                  const float* d_packed, const float* g_loss, float* d_tokens, cudaStream_t st);
+int joint_gather(float* mod, long long cap, float* joint, const int* seq_off, int B, int max_len, int dir, cudaStream_t st);
+int pool_fwd(const float* x, const int* seq_off, int B, float* cls_out, float* patch_mean, int* num, cudaStream_t st);
+int pool_bwd(const float* d_cls, const float* d_patch, const int* seq_off, const int* num, int B, int max_len, float* dx,
+             cudaStream_t st);
+int cls_rows(float* packed, long long cap, const int* seq_off, int B, float* rows, int dir, cudaStream_t st);
+
 }  // namespace edb

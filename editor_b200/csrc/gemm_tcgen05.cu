@@ -35,6 +35,8 @@ struct GemmKernelParams {
     void* out2;
     long long ld_out2;
     float alpha;
+    const float* row_scale;
+    int scale_group;
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -246,16 +248,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int i = 0; i < 32; ++i) v[i] = gelu_exact(v[i]);
                 } else if (p.epi == EPI_RESIDUAL) {
                     const float* a = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ld_aux + col0;
+                    const float rsc = p.row_scale ? p.row_scale[row / p.scale_group] : 1.0f;
                     if (full) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 a4 = *reinterpret_cast<const float4*>(a + i);
-                            v[i] += a4.x; v[i + 1] += a4.y; v[i + 2] += a4.z; v[i + 3] += a4.w;
+                            v[i] = a4.x + rsc * v[i]; v[i + 1] = a4.y + rsc * v[i + 1];
+                            v[i + 2] = a4.z + rsc * v[i + 2]; v[i + 3] = a4.w + rsc * v[i + 3];
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) v[i] += a[i];
+                            if (col0 + i < p.N) v[i] = a[i] + rsc * v[i];
                     }
                 } else if (p.epi == EPI_GELU_BWD) {
                     if (p.aux_f32) {
@@ -422,6 +426,9 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     p.D = g.D; p.ldd = g.ldd; p.out_f32 = g.out_f32; p.epi = g.epilogue;
     p.bias = g.bias; p.aux = g.aux; p.ld_aux = g.ld_aux; p.aux_f32 = g.aux_f32;
     p.out2 = g.out2; p.ld_out2 = g.ld_out2; p.alpha = g.alpha;
+    p.row_scale = g.row_scale; p.scale_group = g.scale_group > 0 ? g.scale_group : 1;
+    if (g.epilogue == EPI_RESIDUAL && (g.aux == nullptr || !g.aux_f32 || !g.out_f32))
+        return edb_set_error(EDB_ERR_SHAPE, "gemm: the residual epilogue needs fp32 aux and fp32 output");
 
     CUtensorMap ta, tb;
     int rc;

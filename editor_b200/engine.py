@@ -1,0 +1,595 @@
+"""Host-side orchestration of the EDITOR hot path over the C ABI (include/editor_b200.h).
+
+Python here is plumbing only: it owns device memory (a flat parameter / gradient arena and named workspace buffers),
+sequences kernel launches on the current CUDA stream and wires the result into autograd.  All arithmetic of the path --
+3-stream ViT-B/16 backbone, SFTS selection, HMA fusion, forward and backward -- runs in hand-written sm_100a kernels.
+The small [B, 768..2304] tail (REDUCE linears, BNNeck heads, OCFR) is listed in DESIGN.md as the next rows to move.
+
+Reference call sites: modeling/make_model.py:150-258 (EDITOR.forward), modeling/backbones/vit_pytorch.py:623-644
+(Trans.forward), :215-220 (Block), :309-352 (BlockMask), modeling/fusion_part/SFTS.py:145-230,
+modeling/fusion_part/Frequency.py:42-84, modeling/fusion_part/OCFR.py:22-84.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import lib
+
+DIM, HEADS, HID, NTOK, NPATCH = 768, 12, 3072, 129, 128
+P_LD = 136                      # pitch of the stored attention maps (129 padded to a 16-byte multiple)
+MAX_SEL = 82                    # <= 24 per modality x 3 + FREQUENCY_KEEP 10 with the default config
+SCALE = 64 ** -0.5
+BF16, FP32 = "bf16", "fp32"
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class _Lin:
+    """One nn.Linear (or the patch conv) as GEMM operands: W is [out, in] row-major, i.e. K-major B operand."""
+
+    def __init__(self, eng, wname, bname):
+        self.eng, self.wname, self.bname = eng, wname, bname
+        a = eng.arena
+        w = a.view(wname)
+        self.out_f, self.in_f = w.shape[0], w.numel() // w.shape[0]
+        self.w32 = w.view(self.out_f, self.in_f)
+        self.w16 = a.view16(wname).view(self.out_f, self.in_f)
+        self.gw = a.gview(wname).view(self.out_f, self.in_f)
+        self.b = a.view(bname) if bname is not None else None
+        self.gb = a.gview(bname) if bname is not None else None
+        self._split = None
+        self._split_version = -1
+
+    def wsplit(self):
+        """[out, 6*in] bf16 three-piece split of the fp32 weight (fp32-faithful path), cached per parameter version."""
+        ver = self.eng.arena.version(self.wname)
+        if self._split is None or ver != self._split_version:
+            if self._split is None:
+                self._split = torch.empty(self.out_f, 6 * self.in_f, dtype=torch.bfloat16, device=self.w32.device)
+            lib.split3(self.w32, self._split, 1)
+            self._split_version = ver
+        return self._split
+
+
+class _Norm:
+    def __init__(self, eng, prefix, eps):
+        a = eng.arena
+        self.g, self.b = a.view(prefix + ".weight"), a.view(prefix + ".bias")
+        self.gg, self.gb = a.gview(prefix + ".weight"), a.gview(prefix + ".bias")
+        self.eps = eps
+
+
+class _BlockP:
+    def __init__(self, eng, n1, attn, n2, mlp, eps, bias):
+        b = (lambda s: s) if bias else (lambda s: None)
+        self.ln1, self.ln2 = _Norm(eng, n1, eps), _Norm(eng, n2, eps)
+        self.qkv = _Lin(eng, attn + ".qkv.weight", b(attn + ".qkv.bias"))
+        self.proj = _Lin(eng, attn + ".proj.weight", b(attn + ".proj.bias"))
+        self.fc1 = _Lin(eng, mlp + ".fc1.weight", b(mlp + ".fc1.bias"))
+        self.fc2 = _Lin(eng, mlp + ".fc2.weight", b(mlp + ".fc2.bias"))
+
+
+class Arena:
+    """All trainable parameters as views of ONE flat fp32 buffer (+ a bf16 shadow and a flat gradient buffer): one
+    cast kernel per step, one allreduce, one optimizer kernel.  ``state_dict`` / ``load_state_dict`` / ``.grad`` keep
+    working because every ``nn.Parameter`` stays a normal parameter whose storage is a slice of the arena."""
+
+    def __init__(self, model, device):
+        self.model = model
+        self.device = device
+        self.names, self.params, self.offsets = [], [], {}
+        off = 0
+        for name, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            self.names.append(name)
+            self.params.append(p)
+            self.offsets[name] = (off, p.numel(), tuple(p.shape))
+            off += _align(p.numel())
+        self.total = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.flat16 = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        for name, p in zip(self.names, self.params):
+            v = self.view(name)
+            v.copy_(p.data)
+            p.data = v
+        self._ptrs = [p.data_ptr() for p in self.params]
+        self._versions = None
+
+    def view(self, name):
+        o, n, shape = self.offsets[name]
+        return self.flat[o:o + n].view(shape)
+
+    def view16(self, name):
+        o, n, shape = self.offsets[name]
+        return self.flat16[o:o + n].view(shape)
+
+    def gview(self, name):
+        o, n, shape = self.offsets[name]
+        return self.grad[o:o + n].view(shape)
+
+    def version(self, name):
+        return self.params[self.names.index(name)]._version
+
+    def intact(self):
+        return all(p.data_ptr() == q for p, q in zip(self.params, self._ptrs))
+
+    def refresh16(self, force=False):
+        vers = [p._version for p in self.params]
+        if force or vers != self._versions:
+            lib.cast_bf16(self.flat, self.flat16, self.total)
+            self._versions = vers
+
+    def attach_grads(self, names=None):
+        """Expose the gradient arena through ``p.grad`` (what GradScaler / torch optimizers of the unchanged caller
+        read, engine/processor.py:94-96)."""
+        for name, p in zip(self.names, self.params):
+            if names is not None and name not in names:
+                continue
+            gv = self.gview(name)
+            if p.grad is None:
+                p.grad = gv
+            elif p.grad.data_ptr() != gv.data_ptr():
+                p.grad.add_(gv)
+
+
+class Workspace:
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        t = self.bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t[:n].view(shape)
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+def _pick_split(tiles, kb_total, sms=148):
+    best, best_eff = 1, 0.0
+    for s in range(1, 17):
+        if s > kb_total:
+            break
+        items = tiles * s
+        waves = (items + sms - 1) // sms
+        eff = items / (waves * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
+
+
+class EditorEngine:
+    def __init__(self, model):
+        self.model = model
+        self.arena = None
+        self.ws = None
+        self.sel = None
+        self.stats = {}
+
+    # ------------------------------------------------------------------ setup
+    def _ensure(self, device):
+        if not torch.cuda.is_available() or device.type != "cuda":
+            raise lib.EdbError("editor_b200 runs on a CUDA device (sm_100a) only; there is no CPU fallback")
+        lib.load()
+        if self.arena is not None and self.arena.device == device and self.arena.intact():
+            return
+        m = self.model
+        self.arena = Arena(m, device)
+        self.ws = Workspace(device)
+        base = "BACKBONE.base."
+        self.patch = _Lin(self, base + "patch_embed.proj.weight", base + "patch_embed.proj.bias")
+        self.bb_blocks = [_BlockP(self, base + "blocks.%d.norm1" % i, base + "blocks.%d.attn" % i,
+                                  base + "blocks.%d.norm2" % i, base + "blocks.%d.mlp" % i, 1e-6, True) for i in range(12)]
+        self.bb_norm = _Norm(self, base + "norm", 1e-6)
+        f = "FUSE_block."
+        self.hma_blocks = [_BlockP(self, f + n1, f + at, f + n2, f + ml, 1e-5, False)
+                           for n1, at, n2, ml in (("normR", "attnR", "normR_", "mlpR"), ("normN", "attnN", "normN_", "mlpN"),
+                                                  ("normT", "attnT", "normT_", "mlpT"), ("norm1", "attn1", "norm2", "mlp"))]
+        self.hma_out = _Norm(self, f + "out_norm", 1e-5)
+        self.bb_names = [n for n in self.arena.names if n.startswith("BACKBONE.base.") and ".fc." not in n]
+        self.hma_names = [n for n in self.arena.names if n.startswith("FUSE_block.")]
+        self.bb_plist = [self.arena.params[self.arena.names.index(n)] for n in self.bb_names]
+        self.hma_plist = [self.arena.params[self.arena.names.index(n)] for n in self.hma_names]
+
+    # ------------------------------------------------------------------ building blocks
+    def _linear(self, x, L, out, rows, prec, epi=lib.EPI_STORE, aux=None, out2=None, row_scale=None, group=1):
+        if prec == BF16:
+            lib.gemm(x, L.w16, out, rows, L.out_f, L.in_f, epilogue=epi, bias=L.b, aux=aux, out2=out2,
+                     row_scale=row_scale, scale_group=group)
+        else:
+            xs = self.ws.get("split_a", (x.shape[0], 6 * L.in_f), torch.bfloat16)
+            lib.split3(x, xs, 0, rows)
+            lib.gemm(xs, L.wsplit(), out, rows, L.out_f, 6 * L.in_f, epilogue=epi, bias=L.b, aux=aux, out2=out2,
+                     row_scale=row_scale, scale_group=group)
+        return out
+
+    def _wgrad(self, dy, x, L, rows):
+        """dW[out,in] += dy[rows,out]^T x[rows,in]   (split-K, fp32 atomic accumulate into the gradient arena)."""
+        tiles = ((L.out_f + 127) // 128) * ((L.in_f + 255) // 256 if L.in_f > 128 else 1)
+        split = _pick_split(tiles, (rows + 63) // 64)
+        lib.gemm(dy, x, L.gw, L.out_f, L.in_f, rows, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=split)
+
+    def _block_fwd(self, x, x1, x2, rows, bp, attn, tag, prec, rs_attn=None, rs_mlp=None, group=1):
+        """One transformer block (vit_pytorch.py:215-220 / :311-317,328-329) on `rows` packed token rows.
+        x, x1, x2: fp32 residual stream before / after attention / after MLP.  Returns what the backward needs."""
+        ws, cap = self.ws, x.shape[0]
+        adt = torch.bfloat16 if prec == BF16 else torch.float32
+        ln1 = ws.get(tag + "ln1", (cap, DIM), adt)
+        m1, r1 = ws.get(tag + "m1", (cap,), torch.float32), ws.get(tag + "r1", (cap,), torch.float32)
+        lib.layernorm_fwd(x, bp.ln1.g, bp.ln1.b, bp.ln1.eps, ln1, m1, r1, rows)
+        qkv = ws.get(tag + "qkv", (cap, 3 * DIM), adt)
+        self._linear(ln1, bp.qkv, qkv, rows, prec)
+        att = ws.get(tag + "att", (cap, DIM), adt)
+        P = attn(qkv, att, tag)
+        self._linear(att, bp.proj, x1, rows, prec, epi=lib.EPI_RESIDUAL, aux=x, row_scale=rs_attn, group=group)
+        ln2 = ws.get(tag + "ln2", (cap, DIM), adt)
+        m2, r2 = ws.get(tag + "m2", (cap,), torch.float32), ws.get(tag + "r2", (cap,), torch.float32)
+        lib.layernorm_fwd(x1, bp.ln2.g, bp.ln2.b, bp.ln2.eps, ln2, m2, r2, rows)
+        pre = ws.get(tag + "pre", (cap, HID), adt)
+        h = ws.get(tag + "h", (cap, HID), adt)
+        self._linear(ln2, bp.fc1, h, rows, prec, epi=lib.EPI_GELU, out2=pre)
+        self._linear(h, bp.fc2, x2, rows, prec, epi=lib.EPI_RESIDUAL, aux=x1, row_scale=rs_mlp, group=group)
+        return dict(x=x, x1=x1, ln1=ln1, m1=m1, r1=r1, qkv=qkv, att=att, P=P, ln2=ln2, m2=m2, r2=r2, pre=pre, h=h)
+
+    def _block_bwd(self, g, gb, rows, bp, sv, attn_bwd, dcol_prev, rs_attn=None, rs_prev=None, group=1):
+        """Backward of `_block_fwd`.  g (fp32) / gb (bf16, already DropPath-scaled): gradient w.r.t. the block output;
+        on return they hold the gradient w.r.t. the block input (gb scaled by `rs_prev`)."""
+        ws, cap = self.ws, g.shape[0]
+        dpre = ws.get("dpre", (cap, HID), torch.bfloat16)
+        lib.gemm(gb, bp.fc2.w16, dpre, rows, HID, DIM, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=sv["pre"])
+        self._wgrad(gb, sv["h"], bp.fc2, rows)
+        if bp.fc1.gb is not None:
+            lib.colsum(dpre, bp.fc1.gb, rows, HID)
+        dln = ws.get("dln", (cap, DIM), torch.bfloat16)
+        lib.gemm(dpre, bp.fc1.w16, dln, rows, DIM, HID, b_mn=True)
+        self._wgrad(dpre, sv["ln2"], bp.fc1, rows)
+        lib.layernorm_bwd(dln, sv["x1"], sv["m2"], sv["r2"], bp.ln2.g, g, g, gb, bp.ln2.gg, bp.ln2.gb, bp.proj.gb, rows,
+                          row_scale=rs_attn, scale_group=group)
+        datt = ws.get("datt", (cap, DIM), torch.bfloat16)
+        lib.gemm(gb, bp.proj.w16, datt, rows, DIM, DIM, b_mn=True)
+        self._wgrad(gb, sv["att"], bp.proj, rows)
+        dqkv = ws.get("dqkv", (cap, 3 * DIM), torch.bfloat16)
+        attn_bwd(sv["qkv"], sv["P"], datt, dqkv)
+        if bp.qkv.gb is not None:
+            lib.colsum(dqkv, bp.qkv.gb, rows, 3 * DIM)
+        lib.gemm(dqkv, bp.qkv.w16, dln, rows, DIM, 3 * DIM, b_mn=True)
+        self._wgrad(dqkv, sv["ln1"], bp.qkv, rows)
+        lib.layernorm_bwd(dln, sv["x"], sv["m1"], sv["r1"], bp.ln1.g, g, g, gb, bp.ln1.gg, bp.ln1.gb, dcol_prev, rows,
+                          row_scale=rs_prev, scale_group=group)
+
+    # ------------------------------------------------------------------ backbone (3 modalities batched: S = 3B sequences)
+    def backbone_forward(self, rgb, ni, ti, cam, prec, keep, droppath=None):
+        """Trans.forward for the three modality batches at once (shared weights, make_model.py:158-160).
+        keep=True stores per-layer activations for the backward.  Returns (tokens [3B,129,768] fp32, saved dict)."""
+        ws = self.ws
+        B, _, H, W = rgb.shape
+        S, R = 3 * B, 3 * B * NTOK
+        adt = torch.bfloat16 if prec == BF16 else torch.float32
+        patches = ws.get("patches", (S * NPATCH, DIM), adt)
+        lib.call("edb_patch_im2col", rgb.data_ptr(), ni.data_ptr(), ti.data_ptr(), B, H, W, patches.data_ptr(), DIM,
+                 int(prec == FP32), lib.stream_ptr())
+        pe = ws.get("pe_out", (S * NPATCH, DIM), torch.float32)
+        self._linear(patches, self.patch, pe, S * NPATCH, prec)
+        a = self.arena
+        base = "BACKBONE.base."
+        sie = a.view(base + "sie_embed") if (base + "sie_embed") in a.offsets else None
+        x = ws.get("x_0", (R, DIM), torch.float32)
+        lib.call("edb_embed_assemble", pe.data_ptr(), a.view(base + "cls_token").data_ptr(),
+                 a.view(base + "pos_embed").data_ptr(), lib.ptr(sie), cam.data_ptr(), self.model.sie_coe, S, B, NPATCH,
+                 x.data_ptr(), lib.stream_ptr())
+        pdt = torch.bfloat16 if prec == BF16 else torch.float32
+        saved, maps = [], []
+        for l, bp in enumerate(self.bb_blocks):
+            tag = "bb%d_" % (l if keep else 0)
+            Pm = ws.get("bbP%d" % l, (S * HEADS, NTOK, P_LD), pdt)
+            maps.append(Pm)
+
+            def attn(qkv, out, _tag, Pm=Pm):
+                lib.attention(qkv, out, Pm, S, HEADS, NTOK, SCALE, fixed_len=NTOK, p_rows=NTOK, ldp=P_LD,
+                              impl=self.stats.get("attn_impl", 0))
+                return Pm
+            x1 = ws.get("x_%d" % (2 * l + 1 if keep else 1), (R, DIM), torch.float32)
+            x2 = ws.get("x_%d" % (2 * l + 2 if keep else 2 - (l & 1) * 2), (R, DIM), torch.float32)
+            rs_a = rs_m = None
+            if droppath is not None:
+                rs_a, rs_m = droppath[2 * l], droppath[2 * l + 1]
+            sv = self._block_fwd(x, x1, x2, R, bp, attn, tag, prec, rs_a, rs_m, NTOK)
+            if keep:
+                saved.append(sv)
+            x = x2
+        tokens = torch.empty(S, NTOK, DIM, dtype=torch.float32, device=rgb.device)
+        mf, rf = ws.get("bb_mf", (R,), torch.float32), ws.get("bb_rf", (R,), torch.float32)
+        lib.layernorm_fwd(x, self.bb_norm.g, self.bb_norm.b, self.bb_norm.eps, tokens.view(R, DIM), mf, rf, R)
+        return tokens, dict(blocks=saved, x_last=x, mf=mf, rf=rf, maps=maps, patches=patches, B=B, cam=cam,
+                            droppath=droppath)
+
+    def backbone_backward(self, sv, d_tokens):
+        ws, a = self.ws, self.arena
+        B = sv["B"]
+        S, R = 3 * B, 3 * B * NTOK
+        dp = sv["droppath"]
+        g = ws.get("g", (R, DIM), torch.float32)
+        gb = ws.get("gb", (R, DIM), torch.bfloat16)
+        last = self.bb_blocks[-1]
+        lib.layernorm_bwd(d_tokens.reshape(R, DIM), sv["x_last"], sv["mf"], sv["rf"], self.bb_norm.g, None, g, gb,
+                          self.bb_norm.gg, self.bb_norm.gb, last.fc2.gb, R,
+                          row_scale=None if dp is None else dp[23], scale_group=NTOK)
+
+        def attn_bwd(qkv, P, datt, dqkv):
+            lib.attention(qkv, None, P, S, HEADS, NTOK, SCALE, fixed_len=NTOK, p_rows=NTOK, ldp=P_LD,
+                          impl=self.stats.get("attn_impl", 0), d_out=datt, d_qkv=dqkv, backward=True)
+        for l in range(11, -1, -1):
+            bp = self.bb_blocks[l]
+            prev_gb = self.bb_blocks[l - 1].fc2.gb if l > 0 else None
+            rs_a = None if dp is None else dp[2 * l]
+            rs_prev = None if (dp is None or l == 0) else dp[2 * l - 1]
+            self._block_bwd(g, gb, R, bp, sv["blocks"][l], attn_bwd, prev_gb, rs_a, rs_prev, NTOK)
+        base = "BACKBONE.base."
+        dpatch = ws.get("dpatch", (S * NPATCH, DIM), torch.bfloat16)
+        dpos = a.gview(base + "pos_embed").view(NTOK, DIM)
+        dsie = a.gview(base + "sie_embed") if (base + "sie_embed") in a.offsets else None
+        lib.call("edb_embed_assemble_bwd", g.data_ptr(), S, B, NPATCH, sv["cam"].data_ptr(), self.model.sie_coe,
+                 dpos.data_ptr(), lib.ptr(dsie), dpatch.data_ptr(), lib.stream_ptr())
+        a.gview(base + "cls_token").view(DIM).add_(dpos[0])
+        lib.colsum(dpos[1:], self.patch.gb, NPATCH, DIM)
+        self._wgrad(dpatch, sv["patches"], self.patch, S * NPATCH)
+
+    # ------------------------------------------------------------------ SFTS selection (no gradient)
+    def select(self, rgb, ni, ti, maps, prec, want_debug=False):
+        """mask_fre | RGB_index | NIR_index | TIR_index as 128-bit sets + the packed-row offsets (SFTS.py:183-190)."""
+        ws, m = self.ws, self.model
+        B, _, H, W = rgb.shape
+        S = 3 * B
+        counts = ws.get("freq_counts", (B, NPATCH), torch.int32)
+        lib.call("edb_freq_counts", rgb.data_ptr(), ni.data_ptr(), ti.data_ptr(), B, H, W, counts.data_ptr(),
+                 lib.stream_ptr())
+        index = torch.empty(B, 4, dtype=torch.int32, device=rgb.device)
+        lib.call("edb_topk_mask", counts.data_ptr(), 0, NPATCH, B, NPATCH, int(m.FREQ_INDEX.keep), index.data_ptr(), 0,
+                 lib.stream_ptr())
+        dbg = {}
+        if want_debug:
+            dbg["counts"] = counts.clone()
+            dbg["mask_fre"] = index.clone()
+            dbg["mod_mask"] = torch.zeros(S, 4, dtype=torch.int32, device=rgb.device)
+            dbg["rows"] = torch.empty(S * HEADS, NPATCH, dtype=torch.float32, device=rgb.device)
+        arr = (ctypes.c_void_p * len(maps))(*[t.data_ptr() for t in maps])
+        lib.call("edb_rollout_topk", arr, len(maps), int(prec == FP32), S, B, HEADS, NTOK, P_LD, int(m.head_keep),
+                 index.data_ptr(), lib.ptr(dbg.get("mod_mask")), lib.ptr(dbg.get("rows")), lib.stream_ptr())
+        seq_off = torch.empty(B + 1, dtype=torch.int32, device=rgb.device)
+        seq_off3 = torch.empty(B + 1, dtype=torch.int32, device=rgb.device)
+        lib.call("edb_index_finalize", index.data_ptr(), B, seq_off.data_ptr(), seq_off3.data_ptr(), lib.stream_ptr())
+        off_host = seq_off.cpu()          # the one host sync of the forward (the reference syncs here too: make_model.py:200)
+        lens = off_host[1:] - off_host[:-1]
+        sel = dict(index=index, seq_off=seq_off, seq_off3=seq_off3, T=int(off_host[-1]), max_len=int(lens.max()), B=B,
+                   debug=dbg)
+        return sel
+
+    # ------------------------------------------------------------------ HMA on packed kept tokens
+    def _varlen_attn(self, seq_off, nseq, max_len, tagP, prec):
+        ws = self.ws
+        ldp = _align(max_len, 8)
+        pdt = torch.bfloat16 if prec == BF16 else torch.float32
+
+        def fwd(qkv, out, tag):
+            Pm = ws.get(tagP + tag, (nseq * HEADS, max_len, ldp), pdt)
+            lib.attention(qkv, out, Pm, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=max_len, ldp=ldp, impl=1)
+            return Pm
+
+        def bwd(qkv, P, datt, dqkv):
+            lib.attention(qkv, None, P, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=max_len, ldp=ldp, impl=1,
+                          d_out=datt, d_qkv=dqkv, backward=True)
+        return fwd, bwd
+
+    def hma_forward(self, tokens, sel, prec, training):
+        """SFTS masking (SFTS.py:208-222) + BlockMask.forward (vit_pytorch.py:309-352) + pooling
+        (make_model.py:186-203) on the packed kept rows.  tokens: [3B,129,768] fp32."""
+        ws = self.ws
+        B, T, ml = sel["B"], sel["T"], sel["max_len"]
+        cap = B * (1 + NPATCH)
+        dev = tokens.device
+        xp = ws.get("hma_xp", (3, cap, DIM), torch.float32)
+        loss_bcc = torch.zeros(1, dtype=torch.float32, device=dev) if training else None
+        lib.call("edb_sfts_pack_fwd", tokens.data_ptr(), sel["index"].data_ptr(), sel["seq_off"].data_ptr(), B, cap,
+                 xp.data_ptr(), lib.ptr(loss_bcc), lib.stream_ptr())
+        afwd, abwd = self._varlen_attn(sel["seq_off"], B, ml, "hmaP", prec)
+        x2all = ws.get("hma_x2", (3, cap, DIM), torch.float32)
+        x1all = ws.get("hma_x1", (3, cap, DIM), torch.float32)
+        saved = []
+        for m in range(3):
+            saved.append(self._block_fwd(xp[m], x1all[m], x2all[m], T, self.hma_blocks[m], afwd, "hma%d_" % m, prec))
+        cls_mid = None
+        if training:
+            cls_mid = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
+            lib.call("edb_cls_rows", x2all.data_ptr(), cap, sel["seq_off"].data_ptr(), B, cls_mid.data_ptr(), 0,
+                     lib.stream_ptr())
+        xj = ws.get("hma_xj", (3 * cap, DIM), torch.float32)
+        lib.call("edb_joint_gather", x2all.data_ptr(), cap, xj.data_ptr(), sel["seq_off"].data_ptr(), B, ml, 0,
+                 lib.stream_ptr())
+        jfwd, jbwd = self._varlen_attn(sel["seq_off3"], B, 3 * ml, "hmaPj", prec)
+        xj1 = ws.get("hma_xj1", (3 * cap, DIM), torch.float32)
+        xj2 = ws.get("hma_xj2", (3 * cap, DIM), torch.float32)
+        svj = self._block_fwd(xj, xj1, xj2, 3 * T, self.hma_blocks[3], jfwd, "hmaJ_", prec)
+        xo = ws.get("hma_xo", (3 * cap, DIM), torch.float32)
+        mo, ro = ws.get("hma_mo", (3 * cap,), torch.float32), ws.get("hma_ro", (3 * cap,), torch.float32)
+        lib.layernorm_fwd(xj2, self.hma_out.g, self.hma_out.b, self.hma_out.eps, xo, mo, ro, 3 * T)
+        cls_out = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
+        patch_mean = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
+        num = torch.empty(B, dtype=torch.int32, device=dev)
+        lib.call("edb_pool_fwd", xo.data_ptr(), sel["seq_off"].data_ptr(), B, cls_out.data_ptr(), patch_mean.data_ptr(),
+                 num.data_ptr(), lib.stream_ptr())
+        sv = dict(mods=saved, joint=svj, xj2=xj2, mo=mo, ro=ro, num=num, abwd=abwd, jbwd=jbwd, cap=cap)
+        return cls_out, patch_mean, cls_mid, loss_bcc, num, sv
+
+    def hma_backward(self, tokens, sel, sv, d_cls, d_patch, d_mid, d_bcc):
+        ws = self.ws
+        B, T, ml, cap = sel["B"], sel["T"], sel["max_len"], sv["cap"]
+        dxo = ws.get("hma_dxo", (3 * cap, DIM), torch.float32)
+        lib.call("edb_pool_bwd", d_cls.data_ptr(), d_patch.data_ptr(), sel["seq_off"].data_ptr(), sv["num"].data_ptr(), B,
+                 ml, dxo.data_ptr(), lib.stream_ptr())
+        gj = ws.get("hma_gj", (3 * cap, DIM), torch.float32)
+        gbj = ws.get("hma_gbj", (3 * cap, DIM), torch.bfloat16)
+        lib.layernorm_bwd(dxo, sv["xj2"], sv["mo"], sv["ro"], self.hma_out.g, None, gj, gbj, self.hma_out.gg,
+                          self.hma_out.gb, None, 3 * T)
+        self._block_bwd(gj, gbj, 3 * T, self.hma_blocks[3], sv["joint"], sv["jbwd"], None)
+        gm = ws.get("hma_gm", (3, cap, DIM), torch.float32)
+        lib.call("edb_joint_gather", gm.data_ptr(), cap, gj.data_ptr(), sel["seq_off"].data_ptr(), B, ml, 1,
+                 lib.stream_ptr())
+        if d_mid is not None:
+            lib.call("edb_cls_rows", gm.data_ptr(), cap, sel["seq_off"].data_ptr(), B, d_mid.data_ptr(), 1,
+                     lib.stream_ptr())
+        gbm = ws.get("hma_gbm", (cap, DIM), torch.bfloat16)
+        for m in range(3):
+            lib.cast_bf16(gm[m], gbm, T * DIM)
+            self._block_bwd(gm[m], gbm, T, self.hma_blocks[m], sv["mods"][m], sv["abwd"], None)
+        d_tokens = torch.empty_like(tokens)
+        lib.call("edb_sfts_pack_bwd", tokens.data_ptr(), sel["index"].data_ptr(), sel["seq_off"].data_ptr(), B, cap,
+                 gm.data_ptr(), lib.ptr(d_bcc), d_tokens.data_ptr(), lib.stream_ptr())
+        return d_tokens
+
+    # ------------------------------------------------------------------ model-level forward
+    def _precision(self, training):
+        p = self.model.precision
+        if p == "auto":
+            return BF16 if (training or torch.is_autocast_enabled("cuda")) else FP32
+        return p
+
+    def _droppath(self, B, device):
+        """Per-sample keep/keep_prob factors in the reference's draw order: for each modality call (RGB, NI, TI), for
+        each block, one torch.rand((B,1,1)) for the attention branch then one for the MLP branch (vit_pytorch.py:52-69,
+        215-220; block 0 has rate 0 -> nn.Identity, :210).  Returned as 24 vectors of length 3B (sequence s = m*B+b)."""
+        rates = self.model.BACKBONE.base.drop_path_rates
+        if max(rates) <= 0.0:
+            return None
+        out = [torch.ones(3 * B, dtype=torch.float32, device=device) for _ in range(24)]
+        for m in range(3):
+            for l, r in enumerate(rates):
+                if r <= 0.0:
+                    continue
+                keep = 1.0 - r
+                for j in range(2):
+                    rnd = torch.rand((B,), dtype=torch.float32, device=device)
+                    out[2 * l + j][m * B:(m + 1) * B] = torch.floor(keep + rnd) / keep
+        return out
+
+    def forward(self, x, cam_label, label, writer, epoch):
+        m = self.model
+        rgb, ni, ti = x["RGB"], x["NI"], x["TI"]
+        self._ensure(rgb.device)
+        for t in (rgb, ni, ti):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.shape != rgb.shape:
+                raise lib.EdbError("inputs must be contiguous float32 [B,3,H,W] CUDA tensors of one shape")
+        if tuple(rgb.shape[2:]) != m.image_size:
+            raise AssertionError("Input image size (%d*%d) doesn't match model (%d*%d)." %
+                                 (rgb.shape[2], rgb.shape[3], m.image_size[0], m.image_size[1]))   # vit_pytorch.py:453-454
+        B = rgb.shape[0]
+        if cam_label is None:
+            cam_label = torch.zeros(B, dtype=torch.int64, device=rgb.device)
+        cam = cam_label.to(torch.int64).contiguous()
+        training = m.training
+        prec = self._precision(training)
+        if training and prec != BF16:
+            raise lib.EdbError("training runs in the bf16 tensor-core mode only (fp32 backward is not implemented)")
+        self.arena.refresh16()
+        if not training:
+            with torch.no_grad():
+                tokens, sv = self.backbone_forward(rgb, ni, ti, cam, prec, keep=False)
+                sel = self.select(rgb, ni, ti, sv["maps"], prec, want_debug=self.stats.get("debug", False))
+                self.sel = sel
+                cls_out, patch_mean, _, _, num, _ = self.hma_forward(tokens, sel, prec, False)
+                self.last = dict(tokens=tokens, num=num)
+                with torch.autocast("cuda", enabled=False):
+                    return self._reduce(cls_out, patch_mean)
+        self.arena.grad.zero_()
+        dp = self._droppath(B, rgb.device)
+        tokens = _BackboneFn.apply(self, rgb, ni, ti, cam, prec, dp, *self.bb_plist)
+        tok = tokens.view(3, B, NTOK, DIM)
+        cls_bb = [tok[i, :, 0] for i in range(3)]
+        if m.AL:
+            ori = torch.cat(cls_bb, dim=-1)
+            ori_score = m.AL_HEAD(m.AL_BN(ori))
+        else:
+            scores = [m.BACKBONE_HEAD(m.BACKBONE_BN(c)) for c in cls_bb]
+        cls_out, patch_mean, cls_mid, loss_bcc = _HMAFn.apply(self, tokens, prec, *self.hma_plist)
+        loss_ocfr = self._ocfr(cls_mid, label)
+        if writer is not None:
+            writer.add_scalar("num_count", self.last["num"].float().mean(), epoch)      # make_model.py:199-200
+        cls4t = self._reduce(cls_out, patch_mean)
+        score = m.FUSE_HEAD(m.FUSE_BN(cls4t))
+        aux = loss_bcc.reshape(()) + loss_ocfr
+        if m.AL:
+            return score, cls4t, ori_score, ori, aux
+        return score, cls4t, scores[0], cls_bb[0], scores[1], cls_bb[1], scores[2], cls_bb[2], aux
+
+    def _reduce(self, cls_out, patch_mean):
+        m = self.model
+        outs = [lin(torch.cat([cls_out[i], patch_mean[i]], dim=-1))
+                for i, lin in enumerate((m.RGB_REDUCE, m.NIR_REDUCE, m.TIR_REDUCE))]          # make_model.py:205-208
+        return torch.cat(outs, dim=-1)
+
+    def _ocfr(self, cls_mid, label):
+        """OCFR.forward (OCFR.py:44-84) without host syncs: per-ID batch centres of the L2-normalised cls tokens, EMA
+        into the memory bank (before the loss, :53), MSE(centres[label], feat).  Equals the reference for the P x K
+        contiguous labels it assumes (:33-36)."""
+        mem = self.model.FUSE_block.memory_cls
+        C = mem.RGB_centers.shape[0]
+        loss = 0
+        with torch.autocast("cuda", enabled=False):
+            ones = torch.ones(label.shape[0], dtype=torch.float32, device=label.device)
+            cnt = torch.zeros(C, dtype=torch.float32, device=label.device).index_add_(0, label, ones)
+            present = (cnt > 0).unsqueeze(1)
+            for i, cen in enumerate((mem.RGB_centers, mem.NIR_centers, mem.TIR_centers)):
+                f = F.normalize(cls_mid[i].float(), dim=1)
+                sums = torch.zeros_like(cen.data).index_add_(0, label, f.detach())
+                bc = sums / cnt.clamp(min=1).unsqueeze(1)
+                cen.data.copy_(torch.where(present, mem.momentum * bc + (1 - mem.momentum) * cen.data, cen.data))
+                loss = loss + F.mse_loss(cen.data[label], f)
+        return loss
+
+
+class _BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, rgb, ni, ti, cam, prec, dp, *params):
+        tokens, sv = eng.backbone_forward(rgb, ni, ti, cam, prec, keep=True, droppath=dp)
+        eng.sel = eng.select(rgb, ni, ti, sv["maps"], prec, want_debug=eng.stats.get("debug", False))
+        ctx.eng, ctx.sv, ctx.nparams = eng, sv, len(params)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, d_tokens):
+        eng = ctx.eng
+        eng.backbone_backward(ctx.sv, d_tokens.contiguous().float())
+        eng.arena.attach_grads(set(eng.bb_names))
+        return (None,) * (7 + ctx.nparams)
+
+
+class _HMAFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, tokens, prec, *params):
+        cls_out, patch_mean, cls_mid, loss_bcc, num, sv = eng.hma_forward(tokens, eng.sel, prec, True)
+        eng.last = dict(num=num, tokens=tokens)
+        ctx.eng, ctx.sv, ctx.sel, ctx.nparams = eng, sv, eng.sel, len(params)
+        ctx.save_for_backward(tokens)
+        return cls_out, patch_mean, cls_mid, loss_bcc
+
+    @staticmethod
+    def backward(ctx, d_cls, d_patch, d_mid, d_bcc):
+        eng = ctx.eng
+        (tokens,) = ctx.saved_tensors
+        z = lambda t, ref: torch.zeros_like(ref) if t is None else t.contiguous().float()   # noqa: E731
+        shape_ref = torch.empty(3, ctx.sel["B"], DIM, device=tokens.device)
+        d_tokens = eng.hma_backward(tokens, ctx.sel, ctx.sv, z(d_cls, shape_ref), z(d_patch, shape_ref),
+                                    None if d_mid is None else d_mid.contiguous().float(),
+                                    None if d_bcc is None else d_bcc.contiguous().float())
+        eng.arena.attach_grads(set(eng.hma_names))
+        return (None, d_tokens, None) + (None,) * ctx.nparams

@@ -60,9 +60,112 @@ typedef struct EdbGemmDesc {
     void* out2; long long ld_out2;     /* EPI_GELU only; same dtype as D */
     float alpha;
     int split_k;                       /* >1 only with EPI_ATOMIC */
+    const float* row_scale;            /* EPI_RESIDUAL only: D = aux + row_scale[row/scale_group]*(acc+bias) -- DropPath   */
+    int scale_group;                   /* (vit_pytorch.py:52-69,217-219); NULL = 1.0                                      */
 } EdbGemmDesc;
 
 int edb_gemm_bf16(const EdbGemmDesc* desc, void* stream);
+
+/* ---- row kernels (HBM-bound) ------------------------------------------------------------------------------ */
+
+/* y = LayerNorm(x) over 768-wide rows; optional per-row mean / rstd for the backward.
+ * Replaces nn.LayerNorm in Block (vit_pytorch.py:206,211,643, eps 1e-6) and BlockMask (:265-296, eps 1e-5). */
+int edb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
+                      long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, void* stream);
+
+/* g_out = g_in + dLN(dy) (g_in may be NULL, may alias g_out); optional bf16 copy of g_out; dgamma/dbeta/dcol are
+ * ACCUMULATED (+=), dcol = column sums of g_out (the bias gradient of the Linear feeding this residual value). */
+size_t edb_layernorm_bwd_workspace_bytes(void);
+int edb_layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
+                      const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg,
+                      void* g_bf16, long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace,
+                      size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, void* stream);
+/* row_scale (optional): g_bf16 and dcol carry row_scale[row/scale_group]*g_out -- the gradient entering a DropPath-scaled
+ * branch (vit_pytorch.py:52-69). */
+
+/* out[n] += sum_r src[r][n]  (bias gradients of nn.Linear, vit_pytorch.py:133-136,181-183) */
+int edb_colsum(const void* src, long long ld, int src_f32, int rows, int n, float* out, void* stream);
+
+/* fp32 -> bf16 (weights once per step, activations) */
+int edb_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
+
+/* fp32 -> 3-piece bf16 split laid out along K for the fp32-faithful GEMM: dst is [rows][6*K] bf16;
+ * role 0 = A-side order, role 1 = B-side order (see rowops.cu).  EDB_PREC_FP32 path only. */
+int edb_split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, void* stream);
+
+/* patches[(m*B+b)*P + p][c*256+ky*16+kx] of the three modality images [B,3,H,W]: the k16/s16 patch conv as a GEMM
+ * operand (PatchEmbed_overlap.forward, vit_pytorch.py:455-457). */
+int edb_patch_im2col(const float* rgb, const float* ni, const float* ti, int B, int H, int W, void* out, long long ldo,
+                     int out_f32, void* stream);
+
+/* x[s][t] = (t==0 ? cls : patch_out[s*P+t-1]) + pos[t] + coe*sie[cam[s%B]]   (Trans.forward, vit_pytorch.py:627-633);
+ * sie may be NULL.  cam is int64[B]. */
+int edb_embed_assemble(const float* patch_out, const float* cls, const float* pos, const float* sie,
+                       const long long* cam, float coe, int S, int B, int P, float* x, void* stream);
+/* dpos += sum_s g;  dsie[cam] += coe*sum_t g;  dpatch (bf16, [S*P][768]) = g[:,1:]  */
+int edb_embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos,
+                           float* dsie, void* dpatch_bf16, void* stream);
+
+/* ---- attention ---------------------------------------------------------------------------------------------- */
+
+/* softmax(q k^T * scale) v per (sequence, head) on a packed [rows][3*heads*64] qkv matrix; optionally stores the
+ * post-softmax maps P (the reference returns them, vit_pytorch.py:195-196; SFTS consumes them, SFTS.py:145-153).
+ * Sequences: seq_off (nseq+1 int32 row offsets, device) or fixed_len.  impl: 0 = tensor-core kernel when the shape
+ * allows (bf16, fixed_len 129), 1 = CUDA-core kernel (any length <= 256, fp32 or bf16 storage).
+ * Also serves AttentionMask (vit_pytorch.py:240-258) on packed kept tokens. */
+typedef struct EdbAttnDesc {
+    const void* qkv; long long ld_qkv;
+    void* out; long long ld_out;
+    void* P; long long p_rows; long long ldp;
+    const int* seq_off; int fixed_len; int nseq; int heads; int max_len;
+    float scale;
+    int f32;            /* storage type of qkv/out/P/d_out/d_qkv: 1 = fp32, 0 = bf16 */
+    int impl;
+    const void* d_out; long long ld_dout;   /* backward */
+    void* d_qkv;                            /* backward, same pitch as qkv */
+} EdbAttnDesc;
+int edb_attention_fwd(const EdbAttnDesc* desc, void* stream);
+int edb_attention_bwd(const EdbAttnDesc* desc, void* stream);
+
+/* ---- SFTS: token selection -------------------------------------------------------------------------------- */
+
+/* counts[b][p] = #pixels of 16x16 window p whose 3-modality/3-channel mean is > 0
+ * (Frequency_based_Token_Selection.forward/.mask, Frequency.py:42-56,65-81; Haar round trip == identity). */
+int edb_freq_counts(const float* rgb, const float* ni, const float* ti, int B, int H, int W, int* counts, void* stream);
+
+/* 128-bit set of torch.topk(vals, k) per row of 128 values (int32 or fp32), CUDA tie rule; store or OR into mask[row][4]
+ * (Frequency.py:58-63; SFTS.py:155-158). */
+int edb_topk_mask(const void* vals, int vals_f32, long long ld, int rows, int n, int k, unsigned* mask, int accumulate,
+                  void* stream);
+
+/* Part_Attention.forward (SFTS.py:145-162): cls row of A_{L-1}...A_0 per (sequence, head), per-head top-k, OR into
+ * index[s % B] (SFTS.py:187-190).  maps: host array of `layers` device pointers, each [(s*heads+h)][p_rows][ldp]. */
+int edb_rollout_topk(const void* const* maps_host, int layers, int maps_f32, int nseq, int B, int heads,
+                     long long p_rows, long long ldp, int k, unsigned* index, unsigned* mod_mask, float* rows_out,
+                     void* stream);
+
+/* seq_off[b] = sum_{b'<b}(1 + popcount(index[b'])), seq_off3 = 3*seq_off (B+1 entries each, device). */
+int edb_index_finalize(const unsigned* index, int B, int* seq_off, int* seq_off3, void* stream);
+
+/* SFTS.forward (SFTS.py:208-222) fused with packing: kept rows (cls + selected) of tokens[3][B][129][768] go to
+ * packed[3][cap][768] at row seq_off[b]+rank; loss_bcc (optional, pre-zeroed) += the three background MSEs. */
+int edb_sfts_pack_fwd(const float* tokens, const unsigned* index, const int* seq_off, int B, long long cap,
+                      float* packed, float* loss_bcc, void* stream);
+int edb_sfts_pack_bwd(const float* tokens, const unsigned* index, const int* seq_off, int B, long long cap,
+                      const float* d_packed, const float* g_loss, float* d_tokens, void* stream);
+
+/* per-modality packed rows <-> joint rows (torch.cat([RGB,NIR,TIR],dim=1), vit_pytorch.py:324); dir 0 mod->joint */
+int edb_joint_gather(float* mod, long long cap, float* joint, const int* seq_off, int B, int max_len, int dir,
+                     void* stream);
+
+/* make_model.py:186-203: cls rows, patch sums / count(RGB rows != 0) from the joint packed HMA output */
+int edb_pool_fwd(const float* x, const int* seq_off, int B, float* cls_out, float* patch_mean, int* num, void* stream);
+int edb_pool_bwd(const float* d_cls, const float* d_patch, const int* seq_off, const int* num, int B, int max_len,
+                 float* dx, void* stream);
+
+/* rows[m][b] = packed[m][seq_off[b]] (dir 0) or packed[m][seq_off[b]] += rows[m][b] (dir 1): HMA cls tokens for OCFR
+ * (vit_pytorch.py:319-323). */
+int edb_cls_rows(float* packed, long long cap, const int* seq_off, int B, float* rows, int dir, void* stream);
 
 #ifdef __cplusplus
 }

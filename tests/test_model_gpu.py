@@ -1,0 +1,98 @@
+"""End-to-end parity of the CUDA path (through the drop-in model surface and the C ABI) against the CPU oracle and the
+committed golden vectors of the unmodified reference."""
+import os
+
+import pytest
+import torch
+
+import __graft_entry__ as ge
+from oracle import editor_oracle as orc
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _bits(idx):
+    idx = idx.cpu()
+    return ((idx.view(-1, 4, 1) >> torch.arange(32).view(1, 1, 32)) & 1).bool().reshape(-1, 128)
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("al", [True, False])
+def test_eval_fp32_matches_oracle_and_reference_golden(al):
+    model, sd, x, label, cam, _ = ge._small_case(al, 4)
+    model = model.cuda().eval()
+    model.engine().stats["debug"] = True
+    xg = {k: v.cuda() for k, v in x.items()}
+    out = model(xg, cam_label=cam.cuda())
+    eng = model.engine()
+    aux = {}
+    with torch.no_grad():
+        ref = orc.editor_forward(sd, x, cam, training=False, al=al, aux=aux)
+    dbg = eng.sel["debug"]
+    assert torch.equal(dbg["counts"].cpu(), orc.frequency_counts(x["RGB"], x["NI"], x["TI"]))     # integer: bit-exact
+    assert torch.equal(_bits(dbg["mask_fre"]), aux["mask_fre"])
+    assert torch.equal(_bits(eng.sel["index"]), aux["index"])                                     # index: bit-exact
+    tok = eng.last["tokens"].view(3, 4, 129, 768).cpu()
+    for m in range(3):
+        assert _rel(tok[m], aux["tokens"][m]) < 1e-3                                              # tolerance: 1e-3 rel (fp32)
+    assert torch.equal(eng.last["num"].cpu().long(), aux["num"])
+    assert out.shape == (4, 2304) and out.dtype == torch.float32
+    assert _rel(out.cpu(), ref) < 1e-3
+    g = torch.load(os.path.join(HERE, "golden", "ref_%s.pt" % ("rgbnt201" if al else "rgbnt100")), weights_only=False)
+    assert torch.equal(_bits(eng.sel["index"]), g["eval_index"])
+    assert _rel(out.cpu(), g["eval_cls4t"]) < 1e-3
+
+
+@pytest.mark.parametrize("al", [True, False])
+def test_train_bf16_forward_backward_matches_oracle(al):
+    model, sd, x, label, cam, _ = ge._small_case(al, 4)
+    model = model.cuda().train()
+    xg = {k: v.cuda() for k, v in x.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = model(xg, label=label.cuda(), cam_label=cam.cuda(), writer=None, epoch=1)
+    loss = orc.reference_loss([o.float() for o in outs], label.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    # oracle (fp32, CPU) on the same inputs/weights, forced to the SAME selection so that the comparison is about arithmetic
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "centers" not in k and "running" not in k
+               and not k.startswith("FREQ_INDEX") else v) for k, v in sd.items()}
+    aux, state = {}, {}
+    ref = orc.editor_forward(sdr, x, cam, label=label, training=True, al=al, aux=aux, state_out=state)
+    same_sel = torch.equal(_bits(model.engine().sel["index"]), aux["index"])
+    n_diff = int((_bits(model.engine().sel["index"]) != aux["index"]).sum())
+    print("bf16 selection bits differing from the fp32 oracle:", n_diff, "of", aux["index"].numel())
+    assert len(outs) == len(ref)
+    rl = orc.reference_loss(ref, label)
+    rl.backward()
+    if same_sel:
+        for a, b in zip(outs, ref):
+            assert a.shape == b.shape
+            assert _rel(a.float().cpu(), b.detach()) < 3e-2          # tolerance: bf16 tensor-core path vs fp32, 1e-2-class
+        assert abs(loss.item() - rl.item()) < 2e-2 * abs(rl.item())
+        worst = 0.0
+        for k, p in model.named_parameters():
+            if sdr[k].grad is None:
+                continue
+            assert p.grad is not None, k
+            gr, gg = sdr[k].grad, p.grad.float().cpu()
+            if gr.norm() < 1e-7:
+                continue
+            err = ((gg - gr).norm() / gr.norm()).item()
+            worst = max(worst, err)
+            assert err < 6e-2, (k, err)
+        print("worst relative gradient error (L2) vs fp32 oracle: %.3e" % worst)
+    for k in state:
+        if "centers" in k and same_sel:
+            got = model.state_dict()[k].cpu()
+            assert _rel(got[label.unique()], state[k][label.unique()]) < 3e-2, k
+
+
+def test_state_dict_schema_and_config_surface():
+    model, sd, *_ = ge._small_case(True, 2)
+    own = model.state_dict()
+    assert list(own.keys()) == list(sd.keys())
+    assert all(own[k].shape == sd[k].shape for k in sd)
