@@ -39,6 +39,10 @@ int edb_colsum(const void* src, long long ld, int src_f32, int rows, int n, floa
     return edb::colsum(src, ld, src_f32, rows, n, out, ST);
 }
 int edb_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream) { return edb::cast_f32_bf16(src, dst, n, ST); }
+int edb_sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr,
+                 float momentum, float wd, float wd_bias, float bias_lr_factor, float gscale, int first, void* stream) {
+    return edb::sgd_step(p, g, buf, p16, flags, n, lr, momentum, wd, wd_bias, bias_lr_factor, gscale, first, ST);
+}
 int edb_split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, void* stream) {
     return edb::split_bf16x3(src, ld, rows, K, dst, role, ST);
 }

@@ -42,6 +42,8 @@ int embed_assemble(const float* patch_out, const float* cls, const float* pos, c
                    float coe, int S, int B, int P, float* x, cudaStream_t st);
 int embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos, float* dsie,
                        void* dpatch_bf16, cudaStream_t st);
+int sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr, float mu,
+             float wd, float wd_bias, float bias_lr_factor, float gscale, int first, cudaStream_t st);
 int attention_simple(const EdbAttnDesc& d, bool bwd, cudaStream_t st);
 int attention_tc_fwd(const EdbAttnDesc& d, cudaStream_t st);
 int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st);

@@ -1,7 +1,632 @@
-// Tensor-core (tcgen05/TMEM/TMA) attention for the 129-token backbone sequences -- placeholder entry points until the
-// kernels land; they fail loudly rather than fall back.
+// Tensor-core attention for the backbone's 129-token sequences (Attention.forward, vit_pytorch.py:184-198) on sm_100a:
+// tcgen05.mma with TMEM accumulators, operands staged by TMA, one CTA per (sequence, head), two CTAs per SM.
+//
+// "129 = 128 + 1": the 128 patch queries form one M=128 MMA tile; the cls query (token 0) is a single row and is
+// computed by one warp on CUDA cores from the same shared-memory K/V tiles.  Keys are padded 129 -> 144 (next multiple of
+// the MMA K step); padded score columns are masked, padded P columns are exact zeros.
+//
+// forward:   S[128x144] = Q K^T (4 MMAs, K=64)  ->  softmax in registers (one thread per query row, exp2)  ->
+//            P (bf16) to swizzled smem + TMA store to HBM (SFTS reads it: SFTS.py:145-153; the backward reuses it)  ->
+//            O[128x64] = P V (9 MMAs over 144 keys, V consumed MN-major straight from its TMA tile)  ->  bf16 rows.
+#include "ptx.cuh"
 #include "abi_internal.h"
+
 namespace edb {
-int attention_tc_fwd(const EdbAttnDesc& d, cudaStream_t st) { return attention_simple(d, false, st); }
-int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st) { return attention_simple(d, true, st); }
+
+constexpr int AT_L = 129;       // tokens per sequence
+constexpr int AT_KP = 144;      // keys padded to a multiple of 16
+constexpr int AT_PLD = 136;     // pitch of P in HBM
+constexpr int AT_HD = 64;
+constexpr uint32_t AT_TILE_Q = 128 * 128;          // bytes: 128 rows x 128 B
+constexpr uint32_t AT_TILE_KV = AT_KP * 128;       // 18432
+constexpr uint32_t AT_CHUNK_P = 128 * 128;         // one 64-key chunk of P: 128 rows x 128 B
+constexpr uint32_t AT_F_SQ = 0, AT_F_SK = AT_TILE_Q, AT_F_SV = AT_F_SK + AT_TILE_KV, AT_F_SP = AT_F_SV + AT_TILE_KV;
+constexpr uint32_t AT_F_BAR = AT_F_SP + 3 * AT_CHUNK_P;
+constexpr uint32_t AT_F_TOTAL = AT_F_BAR + 128 + 1024;
+constexpr uint32_t AT_TM_O = 192;                  // TMEM column of the O accumulator (S occupies [0,144))
+
+struct AttnTcParams {
+    const __nv_bfloat16* qkv; long long ld_qkv;
+    __nv_bfloat16* out; long long ld_out;
+    __nv_bfloat16* P;
+    int H;
+    float scale_log2e;          // scale * log2(e)
+    uint32_t idesc_s, idesc_o;
+};
+
+__global__ void __launch_bounds__(192, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                   const __grid_constant__ CUtensorMap map_p, const AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + AT_F_SQ;
+    uint8_t* sK = smem + AT_F_SK;
+    uint8_t* sV = smem + AT_F_SV;
+    uint8_t* sP = smem + AT_F_SP;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + AT_F_BAR);
+    uint64_t* bar_s = bar_load + 1;
+    uint64_t* bar_p = bar_load + 2;
+    uint64_t* bar_o = bar_load + 3;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_load + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x;                 // seq * H + h
+    const int s = blk / p.H, h = blk % p.H;
+    const int row0 = s * AT_L;                  // first token row of this sequence in the qkv matrix
+    const int HC = p.H * AT_HD;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_q);
+            tma_prefetch_desc(&map_kv);
+            tma_prefetch_desc(&map_p);
+            mbar_init(bar_load, 1);
+            mbar_init(bar_s, 1);
+            mbar_init(bar_p, 128);
+            mbar_init(bar_o, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<256>(tmem_ptr);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_load, AT_TILE_Q + 2 * AT_TILE_KV);
+            tma_load_2d(sQ, &map_q, bar_load, h * AT_HD, row0 + 1);
+            tma_load_2d(sK, &map_kv, bar_load, HC + h * AT_HD, row0);
+            tma_load_2d(sV, &map_kv, bar_load, 2 * HC + h * AT_HD, row0);
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                tc_mma_bf16(tmem, make_smem_desc(aq + k * 32, 0, 1024), make_smem_desc(ak + k * 32, 0, 1024), p.idesc_s,
+                            k > 0);
+            tc_commit(bar_s);
+            mbar_wait(bar_p, 0);
+            tc_fence_after();
+            const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+#pragma unroll
+            for (int k = 0; k < AT_KP / 16; ++k)
+                tc_mma_bf16(tmem + AT_TM_O, make_smem_desc(ap + (k >> 2) * AT_CHUNK_P + (k & 3) * 32, 0, 1024),
+                            make_smem_desc(av + k * 2048, AT_TILE_KV, 1024), p.idesc_o, k > 0);
+            tc_commit(bar_o);
+            // P rows 1..128 of this (seq, head) to HBM; columns >= 136 are clipped by the tensor map
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tma_store_2d(&map_p, sP + c * AT_CHUNK_P, c * 64, blk * AT_L + 1);
+            tma_store_commit();
+            tma_store_wait_all();
+        }
+    } else if (warp == 5) {
+        // ---------------- cls query (token 0) on CUDA cores
+        mbar_wait(bar_load, 0);
+        const __nv_bfloat16* q0 = p.qkv + (size_t)row0 * p.ld_qkv + h * AT_HD;
+        float q[AT_HD];
+#pragma unroll
+        for (int d = 0; d < AT_HD; d += 2) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q0 + d));
+            q[d] = f.x; q[d + 1] = f.y;
+        }
+        float sc[5];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = jj * 32 + lane;
+            float acc = -INFINITY;
+            if (j < AT_L) {
+                acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(sK + sw128(j, c));
+                    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = __bfloat1622float2(hh[t]);
+                        acc += q[c * 8 + 2 * t] * f.x + q[c * 8 + 2 * t + 1] * f.y;
+                    }
+                }
+            }
+            sc[jj] = acc;
+            mx = fmaxf(mx, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            sc[jj] = (jj * 32 + lane < AT_L) ? ex2_approx((sc[jj] - mx) * p.scale_log2e) : 0.f;
+            sum += sc[jj];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        __nv_bfloat16* prow = p.P + (size_t)blk * AT_L * AT_PLD;
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = jj * 32 + lane;
+            const __nv_bfloat16 pb = __float2bfloat16(sc[jj] * inv);
+            sc[jj] = __bfloat162float(pb);
+            if (j < AT_PLD) prow[j] = pb;
+        }
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int jn = (jj < 4) ? 32 : 1;
+            for (int t = 0; t < jn; ++t) {
+                const int j = jj * 32 + t;
+                const float pj = __shfl_sync(0xffffffffu, sc[jj], t);
+                const float2 f = __bfloat1622float2(
+                    *reinterpret_cast<const __nv_bfloat162*>(sV + sw128(j, lane >> 2) + (lane & 3) * 4));
+                o0 += pj * f.x;
+                o1 += pj * f.y;
+            }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(p.out + (size_t)row0 * p.ld_out + h * AT_HD + 2 * lane) =
+            __floats2bfloat162_rn(o0, o1);
+    } else {
+        // ---------------- softmax + epilogue: thread i owns query token i+1 (TMEM lane i)
+        const int i = threadIdx.x;
+        const uint32_t tS = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+        float e[132];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tS + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                e[c * 32 + t] = __uint_as_float(r[t]);
+                mx = fmaxf(mx, e[c * 32 + t]);
+            }
+        }
+        {
+            uint32_t r[16];
+            tmem_ld_32x16(tS + 128, r);
+            tmem_ld_wait();
+            e[128] = __uint_as_float(r[0]);
+            mx = fmaxf(mx, e[128]);
+        }
+        const float mb = mx * p.scale_log2e;
+        float sum = 0.f;
+#pragma unroll
+        for (int t = 0; t < AT_L; ++t) {
+            e[t] = ex2_approx(e[t] * p.scale_log2e - mb);
+            sum += e[t];
+        }
+        const float inv = 1.0f / sum;
+        e[129] = e[130] = e[131] = 0.f;
+#pragma unroll
+        for (int q8 = 0; q8 < AT_KP / 8; ++q8) {       // 18 chunks of 8 keys
+            uint4 u;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int c0 = q8 * 8 + 2 * t;
+                const float a = c0 < AT_L ? e[c0 < 132 ? c0 : 131] * inv : 0.f;
+                const float b = c0 + 1 < AT_L ? e[c0 + 1 < 132 ? c0 + 1 : 131] * inv : 0.f;
+                __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+                w[t] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(sP + (q8 >> 3) * AT_CHUNK_P + sw128(i, q8 & 7)) = u;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_p);
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.out + (size_t)(row0 + 1 + i) * p.ld_out + h * AT_HD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tS + AT_TM_O + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; t += 8) {
+                uint4 u;
+                uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[t + 2 * z]), __uint_as_float(r[t + 2 * z + 1]));
+                    w[z] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+                *reinterpret_cast<uint4*>(orow + c * 32 + t) = u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<256>(tmem);
+}
+
+int attention_tc_fwd(const EdbAttnDesc& d, cudaStream_t st) {
+    if (d.nseq <= 0) return EDB_OK;
+    const long long R = (long long)d.nseq * AT_L;
+    CUtensorMap mq, mkv, mp;
+    EDB_TRY(make_tmap_bf16(&mq, d.qkv, 3LL * d.heads * AT_HD, R, d.ld_qkv, 128));
+    EDB_TRY(make_tmap_bf16(&mkv, d.qkv, 3LL * d.heads * AT_HD, R, d.ld_qkv, AT_KP));
+    EDB_TRY(make_tmap_bf16(&mp, d.P, AT_PLD, (long long)d.nseq * d.heads * AT_L, AT_PLD, 128));
+    AttnTcParams p{};
+    p.qkv = (const __nv_bfloat16*)d.qkv; p.ld_qkv = d.ld_qkv;
+    p.out = (__nv_bfloat16*)d.out; p.ld_out = d.ld_out;
+    p.P = (__nv_bfloat16*)d.P; p.H = d.heads;
+    p.scale_log2e = d.scale * 1.4426950408889634f;
+    p.idesc_s = make_idesc_bf16(128, AT_KP, 0, 0);
+    p.idesc_o = make_idesc_bf16(128, AT_HD, 0, 1);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_F_TOTAL);
+        if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
+        configured = true;
+    }
+    attn_tc_fwd_kernel<<<d.nseq * d.heads, 192, AT_F_TOTAL, st>>>(mq, mkv, mp, p);
+    EDB_CHECK_LAUNCH();
+    return EDB_OK;
+}
+
+
+// ======================================================================================================== backward
+// Per (sequence, head), with the saved bf16 P:   dP = dO V^T;  delta_i = sum_j dP_ij P_ij;  dS = P o (dP - delta) * scale;
+// dV = P^T dO;  dQ = dS K;  dK = dS^T Q.
+//
+// Shared-memory tiles are [144 lines x 128 B] (128-byte swizzle).  Query-indexed tiles (Q, dO, and the lines of P/dS) hold
+// the queries in the order  tok1..tok128, tok0, 15 zero lines  -- a reduction dimension may be permuted freely, and this
+// puts the 128 patch queries on one M=128 tile.  Key-indexed tiles (K, V, columns of P/dS) are in natural order.  The
+// same bytes serve as K-major and as MN-major operands: P/dS [q lines x key columns] is the K-major A of dQ = dS K and the
+// MN-major A of dV = P^T dO / dK = dS^T Q.  dS overwrites P in place.  The cls query row and key 128 (the "+1"s) are
+// handled by two extra warps on CUDA cores.
+constexpr uint32_t BT_TILE = AT_KP * 128;                  // 18432
+constexpr uint32_t BT_SQ = 0, BT_SK = BT_TILE, BT_SV = 2 * BT_TILE, BT_SDO = 3 * BT_TILE, BT_SP = 4 * BT_TILE;
+constexpr uint32_t BT_BAR = 7 * BT_TILE;
+constexpr uint32_t BT_TOTAL = BT_BAR + 128 + 1024;
+constexpr uint32_t BT_TX = 2 * (128 * 128 + 128) + 2 * BT_TILE + 3 * (128 * 128 + 128);
+constexpr uint32_t BT_TM_DP = 0, BT_TM_DV = 192, BT_TM_DQ = 256, BT_TM_DK = 320;
+
+struct AttnTcBwdParams {
+    const __nv_bfloat16* qkv; long long ld_qkv;
+    __nv_bfloat16* d_qkv;
+    int H;
+    float scale;
+    uint32_t idesc_dp, idesc_kk_mn, idesc_k_mn;   // (128x144 K/K), (128x64 MN/MN), (128x64 K/MN)
+};
+
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+            uint4 u;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+                __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[t + 2 * z]), __uint_as_float(r[t + 2 * z + 1]));
+                w[z] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+            *reinterpret_cast<uint4*>(dst + c * 32 + t) = u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(224, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_constant__ CUtensorMap map_q1,
+                   const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_do128,
+                   const __grid_constant__ CUtensorMap map_do1, const __grid_constant__ CUtensorMap map_p128,
+                   const __grid_constant__ CUtensorMap map_p1, const AttnTcBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + BT_SQ;
+    uint8_t* sK = smem + BT_SK;
+    uint8_t* sV = smem + BT_SV;
+    uint8_t* sdO = smem + BT_SDO;
+    uint8_t* sP = smem + BT_SP;            // 3 chunks of 64 keys; becomes dS
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BT_BAR);
+    uint64_t *bar_load = bars, *bar_dp = bars + 1, *bar_dv = bars + 2, *bar_pcol = bars + 3, *bar_ds = bars + 4,
+             *bar_dq = bars + 5, *bar_dk = bars + 6;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x;
+    const int s = blk / p.H, h = blk % p.H;
+    const int row0 = s * AT_L;
+    const int HC = p.H * AT_HD;
+
+    // zero the 15 padding lines (129..143) of the query-indexed tiles
+    for (int t = threadIdx.x; t < 5 * 15 * 8; t += 224) {
+        const int tile = t / 120, rem = t % 120, line = 129 + rem / 8, c = rem % 8;
+        uint8_t* base = tile == 0 ? sQ : (tile == 1 ? sdO : sP + (tile - 2) * BT_TILE);
+        *reinterpret_cast<uint4*>(base + line * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_q128); tma_prefetch_desc(&map_q1); tma_prefetch_desc(&map_kv);
+            tma_prefetch_desc(&map_do128); tma_prefetch_desc(&map_do1); tma_prefetch_desc(&map_p128);
+            tma_prefetch_desc(&map_p1);
+            mbar_init(bar_load, 1);
+            mbar_init(bar_dp, 1);
+            mbar_init(bar_dv, 1);
+            mbar_init(bar_pcol, 1);
+            mbar_init(bar_ds, 128 + 1);
+            mbar_init(bar_dq, 1);
+            mbar_init(bar_dk, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_ptr);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_load, BT_TX);
+            tma_load_2d(sQ, &map_q128, bar_load, h * AT_HD, row0 + 1);
+            tma_load_2d(sQ + 128 * 128, &map_q1, bar_load, h * AT_HD, row0);
+            tma_load_2d(sdO, &map_do128, bar_load, h * AT_HD, row0 + 1);
+            tma_load_2d(sdO + 128 * 128, &map_do1, bar_load, h * AT_HD, row0);
+            tma_load_2d(sK, &map_kv, bar_load, HC + h * AT_HD, row0);
+            tma_load_2d(sV, &map_kv, bar_load, 2 * HC + h * AT_HD, row0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                tma_load_2d(sP + c * BT_TILE, &map_p128, bar_load, c * 64, blk * AT_L + 1);
+                tma_load_2d(sP + c * BT_TILE + 128 * 128, &map_p1, bar_load, c * 64, blk * AT_L);
+            }
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV), ado = smem_u32(sdO), ap = smem_u32(sP);
+            // dP = dO V^T
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                tc_mma_bf16(tmem + BT_TM_DP, make_smem_desc(ado + k * 32, 0, 1024), make_smem_desc(av + k * 32, 0, 1024),
+                            p.idesc_dp, k > 0);
+            tc_commit(bar_dp);
+            // dV = P^T dO   (A: P MN-major over keys 0..127, reduction over the 144 query lines)
+#pragma unroll
+            for (int k = 0; k < AT_KP / 16; ++k)
+                tc_mma_bf16(tmem + BT_TM_DV, make_smem_desc(ap + k * 2048, BT_TILE, 1024),
+                            make_smem_desc(ado + k * 2048, BT_TILE, 1024), p.idesc_kk_mn, k > 0);
+            tc_commit(bar_dv);
+            mbar_wait(bar_ds, 0);
+            tc_fence_after();
+            // dQ = dS K     (A: dS K-major, 3 chunks of 64 keys;  B: K MN-major)
+#pragma unroll
+            for (int k = 0; k < AT_KP / 16; ++k)
+                tc_mma_bf16(tmem + BT_TM_DQ, make_smem_desc(ap + (k >> 2) * BT_TILE + (k & 3) * 32, 0, 1024),
+                            make_smem_desc(ak + k * 2048, BT_TILE, 1024), p.idesc_k_mn, k > 0);
+            tc_commit(bar_dq);
+            // dK = dS^T Q   (A: dS MN-major over keys 0..127;  B: Q MN-major, reduction over the 144 query lines)
+#pragma unroll
+            for (int k = 0; k < AT_KP / 16; ++k)
+                tc_mma_bf16(tmem + BT_TM_DK, make_smem_desc(ap + k * 2048, BT_TILE, 1024),
+                            make_smem_desc(aq + k * 2048, BT_TILE, 1024), p.idesc_kk_mn, k > 0);
+            tc_commit(bar_dk);
+        }
+    } else if (warp == 5) {
+        // ---------------- cls query (token 0 = query line 128) on CUDA cores
+        mbar_wait(bar_load, 0);
+        float g[AT_HD];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sdO + sw128(128, c));
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(hh[t]);
+                g[c * 8 + 2 * t] = f.x; g[c * 8 + 2 * t + 1] = f.y;
+            }
+        }
+        float ds[5];
+        float dsum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = jj * 32 + lane;
+            float acc = 0.f, pv = 0.f;
+            if (j < AT_KP) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(sV + sw128(j, c));
+                    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = __bfloat1622float2(hh[t]);
+                        acc += g[c * 8 + 2 * t] * f.x + g[c * 8 + 2 * t + 1] * f.y;
+                    }
+                }
+                pv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                    sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2));
+                if (pv == 0.f) acc = 0.f;       // padded keys: garbage V rows must not leak through 0 * inf
+            }
+            ds[jj] = acc;                        // dP_0j for now
+            dsum += acc * pv;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        mbar_wait(bar_dv, 0);                    // P is no longer read by the dV MMA
+        mbar_wait(bar_pcol, 0);                  // ... nor by the key-128 warp
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = jj * 32 + lane;
+            if (j < AT_KP) {
+                __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) +
+                                                                      (j & 7) * 2);
+                const float pv = __bfloat162float(*ptr);
+                const __nv_bfloat16 d16 = __float2bfloat16(pv * (ds[jj] - dsum) * p.scale);
+                *ptr = d16;
+                ds[jj] = __bfloat162float(d16);
+            } else {
+                ds[jj] = 0.f;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ds);
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int jn = (jj < 4) ? 32 : 1;
+            for (int t = 0; t < jn; ++t) {
+                const int j = jj * 32 + t;
+                const float dj = __shfl_sync(0xffffffffu, ds[jj], t);
+                const float2 f = __bfloat1622float2(
+                    *reinterpret_cast<const __nv_bfloat162*>(sK + sw128(j, lane >> 2) + (lane & 3) * 4));
+                o0 += dj * f.x;
+                o1 += dj * f.y;
+            }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(p.d_qkv + (size_t)row0 * p.ld_qkv + h * AT_HD + 2 * lane) =
+            __floats2bfloat162_rn(o0, o1);
+    } else if (warp == 6) {
+        // ---------------- key 128 (the 129th key) on CUDA cores: dV[128] = sum_i P[i][128] dO[i], dK[128] = sum_i dS[i][128] Q[i]
+        mbar_wait(bar_load, 0);
+        float col[5];
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+            const int i = ii * 32 + lane;        // query line
+            col[ii] = i < AT_L ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sP + 2 * BT_TILE + sw128(i, 0))) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pcol);
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+            const int in = (ii < 4) ? 32 : 1;
+            for (int t = 0; t < in; ++t) {
+                const int i = ii * 32 + t;
+                const float pj = __shfl_sync(0xffffffffu, col[ii], t);
+                const float2 f = __bfloat1622float2(
+                    *reinterpret_cast<const __nv_bfloat162*>(sdO + sw128(i, lane >> 2) + (lane & 3) * 4));
+                o0 += pj * f.x;
+                o1 += pj * f.y;
+            }
+        }
+        __nv_bfloat16* krow = p.d_qkv + (size_t)(row0 + 128) * p.ld_qkv + h * AT_HD;
+        *reinterpret_cast<__nv_bfloat162*>(krow + 2 * HC + 2 * lane) = __floats2bfloat162_rn(o0, o1);
+        mbar_wait(bar_ds, 0);
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+            const int i = ii * 32 + lane;
+            col[ii] = i < AT_L ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sP + 2 * BT_TILE + sw128(i, 0))) : 0.f;
+        }
+        o0 = o1 = 0.f;
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+            const int in = (ii < 4) ? 32 : 1;
+            for (int t = 0; t < in; ++t) {
+                const int i = ii * 32 + t;
+                const float dj = __shfl_sync(0xffffffffu, col[ii], t);
+                const float2 f = __bfloat1622float2(
+                    *reinterpret_cast<const __nv_bfloat162*>(sQ + sw128(i, lane >> 2) + (lane & 3) * 4));
+                o0 += dj * f.x;
+                o1 += dj * f.y;
+            }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(krow + HC + 2 * lane) = __floats2bfloat162_rn(o0, o1);
+    } else {
+        // ---------------- thread i: query line i (token i+1) for dS / dQ, key i (token i) for dK / dV
+        const int i = threadIdx.x;
+        const uint32_t tB = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        mbar_wait(bar_load, 0);
+        mbar_wait(bar_dp, 0);
+        tc_fence_after();
+        float delta = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {            // 32 score columns per pass (the last pass: 16)
+            uint32_t r[32];
+            if (c < 4) tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
+            else tmem_ld_32x16(tB + BT_TM_DP + 128, *reinterpret_cast<uint32_t(*)[16]>(r));
+            tmem_ld_wait();
+            const int nq = c < 4 ? 4 : 2;
+#pragma unroll
+            for (int q = 0; q < nq; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = __bfloat1622float2(hh[t]);
+                    if (f.x != 0.f) delta += f.x * __uint_as_float(r[q * 8 + 2 * t]);
+                    if (f.y != 0.f) delta += f.y * __uint_as_float(r[q * 8 + 2 * t + 1]);
+                }
+            }
+        }
+        mbar_wait(bar_dv, 0);
+        mbar_wait(bar_pcol, 0);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            uint32_t r[32];
+            if (c < 4) tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
+            else tmem_ld_32x16(tB + BT_TM_DP + 128, *reinterpret_cast<uint32_t(*)[16]>(r));
+            tmem_ld_wait();
+            const int nq = c < 4 ? 4 : 2;
+#pragma unroll
+            for (int q = 0; q < nq; ++q) {
+                uint4* ptr = reinterpret_cast<uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                uint4 u = *ptr;
+                __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = __bfloat1622float2(hh[t]);
+                    const float a = f.x != 0.f ? f.x * (__uint_as_float(r[q * 8 + 2 * t]) - delta) * p.scale : 0.f;
+                    const float b = f.y != 0.f ? f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale : 0.f;
+                    hh[t] = __floats2bfloat162_rn(a, b);
+                }
+                *ptr = u;
+            }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_ds);
+        tc_fence_after();
+        __nv_bfloat16* krow = p.d_qkv + (size_t)(row0 + i) * p.ld_qkv + h * AT_HD;
+        store_row64_bf16(krow + 2 * HC, tB + BT_TM_DV);                       // dV[key i]
+        mbar_wait(bar_dq, 0);
+        tc_fence_after();
+        store_row64_bf16(p.d_qkv + (size_t)(row0 + 1 + i) * p.ld_qkv + h * AT_HD, tB + BT_TM_DQ);   // dQ[token i+1]
+        mbar_wait(bar_dk, 0);
+        tc_fence_after();
+        store_row64_bf16(krow + HC, tB + BT_TM_DK);                           // dK[key i]
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st) {
+    if (d.nseq <= 0) return EDB_OK;
+    const long long R = (long long)d.nseq * AT_L;
+    const long long W3 = 3LL * d.heads * AT_HD, W1 = (long long)d.heads * AT_HD;
+    CUtensorMap mq128, mq1, mkv, mdo128, mdo1, mp128, mp1;
+    EDB_TRY(make_tmap_bf16(&mq128, d.qkv, W3, R, d.ld_qkv, 128));
+    EDB_TRY(make_tmap_bf16(&mq1, d.qkv, W3, R, d.ld_qkv, 1));
+    EDB_TRY(make_tmap_bf16(&mkv, d.qkv, W3, R, d.ld_qkv, AT_KP));
+    EDB_TRY(make_tmap_bf16(&mdo128, d.d_out, W1, R, d.ld_dout, 128));
+    EDB_TRY(make_tmap_bf16(&mdo1, d.d_out, W1, R, d.ld_dout, 1));
+    EDB_TRY(make_tmap_bf16(&mp128, d.P, AT_PLD, (long long)d.nseq * d.heads * AT_L, AT_PLD, 128));
+    EDB_TRY(make_tmap_bf16(&mp1, d.P, AT_PLD, (long long)d.nseq * d.heads * AT_L, AT_PLD, 1));
+    AttnTcBwdParams p{};
+    p.qkv = (const __nv_bfloat16*)d.qkv; p.ld_qkv = d.ld_qkv; p.d_qkv = (__nv_bfloat16*)d.d_qkv;
+    p.H = d.heads; p.scale = d.scale;
+    p.idesc_dp = make_idesc_bf16(128, AT_KP, 0, 0);
+    p.idesc_kk_mn = make_idesc_bf16(128, AT_HD, 1, 1);
+    p.idesc_k_mn = make_idesc_bf16(128, AT_HD, 0, 1);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_TOTAL);
+        if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
+        configured = true;
+    }
+    attn_tc_bwd_kernel<<<d.nseq * d.heads, 224, BT_TOTAL, st>>>(mq128, mq1, mkv, mdo128, mdo1, mp128, mp1, p);
+    EDB_CHECK_LAUNCH();
+    return EDB_OK;
+}
+
 }  // namespace edb

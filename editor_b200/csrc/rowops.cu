@@ -415,4 +415,42 @@ int embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam
     return EDB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ fused SGD-momentum
+// torch.optim.SGD semantics of solver/make_optimizer.py:6-22 over the flat arena: g += wd*p; buf = mu*buf + g (buf = g on
+// the first step); p -= lr*buf, with lr*bias_lr_factor and wd_bias on 64-element chunks flagged as bias.  Also refreshes the
+// bf16 shadow of the parameters and scales the incoming gradient (1/world_size after the allreduce).
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                           __nv_bfloat16* __restrict__ p16, const unsigned char* __restrict__ flags, size_t n4, float lr,
+                           float mu, float wd, float wd_bias, float bias_lr_factor, float gscale, int first) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned char f = flags[i >> 4];
+        if (f & 2) continue;                        // frozen / padding chunk
+        const float l = (f & 1) ? lr * bias_lr_factor : lr, w = (f & 1) ? wd_bias : wd;
+        float4 pv = load4(p + i * 4);
+        const float4 gv = load4(g + i * 4);
+        float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : load4(buf + i * 4);
+        const float gx = gv.x * gscale + w * pv.x, gy = gv.y * gscale + w * pv.y, gz = gv.z * gscale + w * pv.z,
+                    gw = gv.w * gscale + w * pv.w;
+        bv.x = first ? gx : mu * bv.x + gx; bv.y = first ? gy : mu * bv.y + gy;
+        bv.z = first ? gz : mu * bv.z + gz; bv.w = first ? gw : mu * bv.w + gw;
+        pv.x -= l * bv.x; pv.y -= l * bv.y; pv.z -= l * bv.z; pv.w -= l * bv.w;
+        store4(buf + i * 4, bv.x, bv.y, bv.z, bv.w);
+        store4(p + i * 4, pv.x, pv.y, pv.z, pv.w);
+        store4(p16 + i * 4, pv.x, pv.y, pv.z, pv.w);
+    }
+}
+
+int sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr, float mu,
+             float wd, float wd_bias, float bias_lr_factor, float gscale, int first, cudaStream_t st) {
+    if (n == 0) return EDB_OK;
+    if (n % 64) return edb_set_error(EDB_ERR_ALIGN, "sgd: arena length must be a multiple of 64");
+    const size_t n4 = n / 4;
+    size_t blocks = (n4 + 255) / 256;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+    sgd_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, buf, (__nv_bfloat16*)p16, flags, n4, lr, mu, wd, wd_bias,
+                                                bias_lr_factor, gscale, first);
+    EDB_CHECK_LAUNCH();
+    return EDB_OK;
+}
+
 }  // namespace edb

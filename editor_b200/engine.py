@@ -45,7 +45,7 @@ class _Lin:
 
     def wsplit(self):
         """[out, 6*in] bf16 three-piece split of the fp32 weight (fp32-faithful path), cached per parameter version."""
-        ver = self.eng.arena.version(self.wname)
+        ver = (self.eng.arena.version(self.wname), self.eng.arena.generation)
         if self._split is None or ver != self._split_version:
             if self._split is None:
                 self._split = torch.empty(self.out_f, 6 * self.in_f, dtype=torch.bfloat16, device=self.w32.device)
@@ -99,6 +99,7 @@ class Arena:
             p.data = v
         self._ptrs = [p.data_ptr() for p in self.params]
         self._versions = None
+        self.generation = 0          # bumped by the fused optimizer kernel (it updates parameters without torch knowing)
 
     def view(self, name):
         o, n, shape = self.offsets[name]

@@ -61,6 +61,8 @@ SIGNATURES = {
                                   c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp, c_int, c_vp]),
     "edb_colsum": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_vp, c_vp]),
     "edb_cast_f32_bf16": (c_int, [c_vp, c_vp, c_sz, c_vp]),
+    "edb_sgd_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_float, c_float, c_float, c_float, c_float, c_float,
+                             c_int, c_vp]),
     "edb_split_bf16x3": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_int, c_vp]),
     "edb_patch_im2col": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp]),
     "edb_embed_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_int, c_int, c_int, c_vp, c_vp]),
@@ -116,6 +118,7 @@ def _f32(t):
 
 
 launch_count = 0   # kernels launched through the C ABI (bench.py reports it as gpu_launches)
+gemm_timing = None  # bench.py sets this to a list to collect (flops, start_event, end_event) per GEMM launch
 
 
 def call(name, *args):
@@ -142,6 +145,13 @@ def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None
     d.split_k = split_k
     d.row_scale = row_scale.data_ptr() if row_scale is not None else None
     d.scale_group = scale_group
+    if gemm_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("edb_gemm_bf16", ctypes.byref(d), stream_ptr())
+        e1.record()
+        gemm_timing.append((2.0 * M * N * K, e0, e1))
+        return D
     call("edb_gemm_bf16", ctypes.byref(d), stream_ptr())
     return D
 

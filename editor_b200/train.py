@@ -1,0 +1,87 @@
+"""Training step around the hot path: loss (layers/make_loss.py:36-56 as called by engine/processor.py:82-92), one
+gradient allreduce over the flat arena (the one collective of the path, processor.py:47-50) and the fused SGD-momentum
+update (solver/make_optimizer.py:6-22).  Rows f-1 / f-2 of SURVEY.md section 8: the loss is still plain torch ops."""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import lib
+
+
+def label_smooth_ce(logits, target, eps=0.1):
+    """CrossEntropyLabelSmooth (layers/softmax_loss.py:23-34) without the reference's .cpu() round trip."""
+    logp = F.log_softmax(logits.float(), dim=1)
+    C = logits.shape[1]
+    nll = -logp.gather(1, target.unsqueeze(1)).squeeze(1)
+    smooth = -logp.sum(1) / C
+    return ((1 - eps) * nll + eps * smooth).sum() / logits.shape[0]
+
+
+def triplet_soft_margin(feat, label):
+    """TripletLoss(margin=None): batch-hard mining + SoftMarginLoss (layers/triplet_loss.py:16-31,51-105,122-136)."""
+    feat = feat.float()
+    xx = feat.pow(2).sum(1, keepdim=True)
+    dist_m = (xx + xx.t() - 2 * feat @ feat.t()).clamp(min=1e-12).sqrt()
+    same = label.unsqueeze(0) == label.unsqueeze(1)
+    ap = torch.where(same, dist_m, dist_m.new_full((), -1e30)).max(1).values
+    an = torch.where(~same, dist_m, dist_m.new_full((), 1e30)).min(1).values
+    return F.soft_margin_loss(an - ap, torch.ones_like(an))
+
+
+def editor_loss(outputs, label, id_w=1.0, tri_w=1.0):
+    """engine/processor.py:82-92: sum over (score, feat) pairs + trailing aux loss."""
+    with torch.autocast("cuda", enabled=False):
+        total = outputs[-1].float()
+        for i in range(0, len(outputs) - 1, 2):
+            total = total + id_w * label_smooth_ce(outputs[i], label) + tri_w * triplet_soft_margin(outputs[i + 1], label)
+    return total
+
+
+class Trainer:
+    """forward -> loss -> backward -> allreduce(arena) -> fused SGD, one process per GPU."""
+
+    def __init__(self, model, lr=0.001, momentum=0.9, weight_decay=1e-4, weight_decay_bias=1e-4, bias_lr_factor=2.0):
+        self.model = model
+        self.lr, self.momentum, self.wd, self.wd_bias, self.blf = lr, momentum, weight_decay, weight_decay_bias, bias_lr_factor
+        self.mom = None
+        self.flags = None
+        self.first = True
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def _setup(self, arena):
+        if self.mom is not None and self.mom.numel() == arena.total and self.mom.device == arena.flat.device:
+            return
+        self.mom = torch.zeros_like(arena.flat)
+        flags = torch.full((arena.total // 64,), 2, dtype=torch.uint8)        # padding chunks are skipped
+        for name in arena.names:
+            o, n, _ = arena.offsets[name]
+            c0, c1 = o // 64, (o + n + 63) // 64
+            unused = name.startswith("BACKBONE.base.fc.")                       # never used by EDITOR (vit_pytorch.py:522)
+            flags[c0:c1] = 2 if unused else (1 if "bias" in name else 0)        # make_optimizer.py:12-15
+        self.flags = flags.to(arena.flat.device)
+        self.first = True
+        self.tail = [(n, p) for n, p in zip(arena.names, arena.params)
+                     if not (n.startswith("BACKBONE.base.") or n.startswith("FUSE_block."))]
+
+    def step(self, x, label, cam, writer=None, epoch=1):
+        model = self.model
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outputs = model(x, label=label, cam_label=cam, view_label=None, img_path=None, writer=writer, epoch=epoch)
+            loss = editor_loss(outputs, label)
+        for _, p in getattr(self, "tail", []):
+            p.grad = None
+        loss.backward()
+        arena = model.engine().arena
+        self._setup(arena)
+        for n, p in self.tail:                                  # tail gradients (torch autograd) into the arena
+            if p.grad is not None and p.grad.data_ptr() != arena.gview(n).data_ptr():
+                arena.gview(n).copy_(p.grad)
+        if self.world > 1:
+            dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM)
+        lib.call("edb_sgd_step", arena.flat.data_ptr(), arena.grad.data_ptr(), self.mom.data_ptr(),
+                 arena.flat16.data_ptr(), self.flags.data_ptr(), arena.total, self.lr, self.momentum, self.wd,
+                 self.wd_bias, self.blf, 1.0 / self.world, int(self.first), lib.stream_ptr())
+        arena.generation += 1
+        arena._versions = [p._version for p in arena.params]   # the bf16 shadow was rewritten by the optimizer kernel
+        self.first = False
+        return loss, outputs

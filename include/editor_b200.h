@@ -89,6 +89,13 @@ int edb_colsum(const void* src, long long ld, int src_f32, int rows, int n, floa
 /* fp32 -> bf16 (weights once per step, activations) */
 int edb_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
 
+/* Fused SGD-momentum over the flat parameter arena (torch.optim.SGD semantics of
+ * solver/make_optimizer.py:6-22: one group per tensor, bias lr x BIAS_LR_FACTOR, weight decay added to the gradient).
+ * flags: one byte per 64-element chunk (bit0 = bias group, bit1 = skip).  Also rewrites the bf16 shadow p16 and applies
+ * gscale to the gradient (1/world_size after the data-parallel allreduce). */
+int edb_sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr,
+                 float momentum, float wd, float wd_bias, float bias_lr_factor, float gscale, int first, void* stream);
+
 /* fp32 -> 3-piece bf16 split laid out along K for the fp32-faithful GEMM: dst is [rows][6*K] bf16;
  * role 0 = A-side order, role 1 = B-side order (see rowops.cu).  EDB_PREC_FP32 path only. */
 int edb_split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, void* stream);

@@ -183,11 +183,15 @@ def backbone(img, cam, sd, droppath=None, depth=12):
 
 
 # --------------------------------------------------------------------------------------- SFTS
-def sfts(feats, maps, mask_fre, head_keep=2, training=False, full_rollout=False):
-    """SFTS.forward (SFTS.py:181-230).  feats/maps: 3-lists (RGB, NIR, TIR).  Returns (3 masked feats, index, bcc)."""
+def sfts(feats, maps, mask_fre, head_keep=2, training=False, full_rollout=False, force_index=None):
+    """SFTS.forward (SFTS.py:181-230).  feats/maps: 3-lists (RGB, NIR, TIR).  Returns (3 masked feats, index, bcc).
+    ``force_index`` (tests only): use this bool [B,128] selection instead of the computed one, so that a reduced-
+    precision run whose top-k flipped on a near-tie can still be compared arithmetically."""
     idx = mask_fre.clone()
     for m in maps:
         idx |= part_attention_mask(m, head_keep, full_rollout)
+    if force_index is not None:
+        idx = force_index.clone()
     index = idx.unsqueeze(-1)
     out = [torch.cat([f[:, :1], f[:, 1:] * index], dim=1) for f in feats]
     loss = None
@@ -292,7 +296,7 @@ def pool_reduce(x, sd):
 
 
 def editor_forward(sd, x, cam_label, label=None, training=False, al=True, head_keep=2, freq_keep=10,
-                   faithful=True, droppath=None, state_out=None, aux=None):
+                   faithful=True, droppath=None, state_out=None, aux=None, force_index=None):
     """EDITOR.forward (make_model.py:150-258).  ``x`` = {'RGB','NI','TI'} float32 [B,3,H,W] CPU tensors.
 
     eval  -> cls4t [B,2304]
@@ -321,7 +325,7 @@ def editor_forward(sd, x, cam_label, label=None, training=False, al=True, head_k
                 if state_out is not None:
                     cur.update({k: v for k, v in state_out.items() if k.startswith("BACKBONE_BN")})
                 bb_scores.append(F.linear(_bn(c, cur, "BACKBONE_BN", True, state_out), sd["BACKBONE_HEAD.weight"]))
-    feats_s, index, loss_bcc = sfts(feats, maps, mask_fre, head_keep, training)
+    feats_s, index, loss_bcc = sfts(feats, maps, mask_fre, head_keep, training, force_index=force_index)
     centers = None
     if training:
         centers = [sd["FUSE_block.memory_cls.%s_centers" % m].clone() for m in ("RGB", "NIR", "TIR")]

@@ -1,0 +1,253 @@
+"""Each C-ABI op against a plain torch fp32 computation of the same op (tight tolerances: these pin the backward
+formulas that the bf16 end-to-end test can only check to 1e-2)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import editor_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("rows", [1, 129, 1000])
+def test_layernorm_fwd_bwd(rows):
+    from editor_b200 import lib
+    x = (torch.randn(rows, 768, generator=_g(1)) * 2 + 0.3).cuda()
+    gam, bet = (1 + 0.1 * torch.randn(768, generator=_g(2))).cuda(), (0.1 * torch.randn(768, generator=_g(3))).cuda()
+    y = torch.empty(rows, 768, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    lib.layernorm_fwd(x, gam, bet, 1e-6, y, mean, rstd)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (768,), gr, br, 1e-6)
+    assert _rel(y, ref.detach()) < 1e-5
+    yb = torch.empty(rows, 768, dtype=torch.bfloat16, device="cuda")
+    lib.layernorm_fwd(x, gam, bet, 1e-6, yb)
+    assert _rel(yb.float(), ref.detach()) < 1e-2
+    dy = torch.randn(rows, 768, generator=_g(4)).cuda()
+    g_in = torch.randn(rows, 768, generator=_g(5)).cuda()
+    scale = (torch.rand((rows + 128) // 129, generator=_g(6)) + 0.5).cuda()
+    ref.backward(dy)
+    g_out = torch.empty_like(x)
+    gb16 = torch.empty(rows, 768, dtype=torch.bfloat16, device="cuda")
+    dgam, dbet, dcol = (torch.zeros(768, device="cuda") for _ in range(3))
+    lib.layernorm_bwd(dy, x, mean, rstd, gam, g_in, g_out, gb16, dgam, dbet, dcol, row_scale=scale, scale_group=129)
+    want = g_in + xr.grad
+    assert _rel(g_out, want) < 1e-4
+    rs = scale.repeat_interleave(129)[:rows].unsqueeze(1)
+    assert _rel(gb16.float(), want * rs) < 1e-2
+    assert _rel(dgam, gr.grad) < 1e-4 and _rel(dbet, br.grad) < 1e-4
+    assert _rel(dcol, (want * rs).sum(0)) < 1e-4
+    # bf16 dy, in-place residual gradient
+    dyb = dy.to(torch.bfloat16)
+    g2 = g_in.clone()
+    lib.layernorm_bwd(dyb, x, mean, rstd, gam, g2, g2, None, dgam, dbet, None)
+    xr2 = x.clone().requires_grad_(True)
+    F.layer_norm(xr2, (768,), gam, bet, 1e-6).backward(dyb.float())
+    assert _rel(g2, g_in + xr2.grad) < 1e-4
+
+
+def test_colsum_cast_split_gemm_fp32_faithful():
+    from editor_b200 import lib
+    src = torch.randn(1000, 3072, generator=_g(1)).cuda()
+    out = torch.zeros(3072, device="cuda")
+    lib.colsum(src.to(torch.bfloat16), out)
+    assert _rel(out, src.to(torch.bfloat16).float().sum(0)) < 1e-4
+    out.zero_()
+    lib.colsum(src, out)
+    assert _rel(out, src.sum(0)) < 1e-4
+    # 3-piece bf16 split GEMM reproduces an fp32 matmul to ~1e-5 (EDB_PREC_FP32 path): the six cross products carry
+    # 24 mantissa bits; what remains is the tensor core's fp32 accumulation over K = 6*768
+    M, N, K = 300, 768, 768
+    A, W = torch.randn(M, K, generator=_g(2)).cuda(), (0.05 * torch.randn(N, K, generator=_g(3))).cuda()
+    As = torch.empty(M, 6 * K, dtype=torch.bfloat16, device="cuda")
+    Ws = torch.empty(N, 6 * K, dtype=torch.bfloat16, device="cuda")
+    lib.split3(A, As, 0)
+    lib.split3(W, Ws, 1)
+    D = torch.empty(M, N, device="cuda")
+    lib.gemm(As, Ws, D, M, N, 6 * K)
+    ref = (A.double() @ W.double().t()).float()
+    assert _rel(D, ref) < 2e-5
+    assert _rel(D, A.to(torch.bfloat16).float() @ W.to(torch.bfloat16).float().t()) > 1e-3   # plain bf16 is 100x worse
+
+
+@pytest.mark.parametrize("H,W", [(256, 128), (128, 256)])
+def test_patch_embed_matches_conv(H, W):
+    from editor_b200 import lib
+    B = 3
+    imgs = [torch.randn(B, 3, H, W, generator=_g(i)).cuda() for i in range(3)]
+    patches = torch.empty(3 * B * 128, 768, device="cuda")
+    lib.call("edb_patch_im2col", imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), B, H, W, patches.data_ptr(),
+             768, 1, lib.stream_ptr())
+    wconv = (0.02 * torch.randn(768, 3, 16, 16, generator=_g(7))).cuda()
+    ref = torch.cat([F.conv2d(i, wconv, stride=16).flatten(2).transpose(1, 2) for i in imgs], 0)   # [3B,128,768]
+    got = (patches @ wconv.view(768, -1).t()).view(3 * B, 128, 768)
+    assert _rel(got, ref) < 1e-4
+    cls, pos = torch.randn(768, generator=_g(8)).cuda(), torch.randn(129, 768, generator=_g(9)).cuda()
+    sie = torch.randn(4, 768, generator=_g(10)).cuda()
+    cam = torch.tensor([0, 3, 1]).cuda()
+    x = torch.empty(3 * B, 129, 768, device="cuda")
+    lib.call("edb_embed_assemble", got.data_ptr(), cls.data_ptr(), pos.data_ptr(), sie.data_ptr(), cam.data_ptr(), 3.0,
+             3 * B, B, 128, x.data_ptr(), lib.stream_ptr())
+    want = torch.cat([cls.expand(3 * B, 1, 768), got], 1) + pos + 3.0 * sie[cam.repeat(3)].unsqueeze(1)
+    assert _rel(x, want) < 1e-6
+    g = torch.randn(3 * B, 129, 768, generator=_g(11)).cuda()
+    dpos, dsie = torch.zeros(129, 768, device="cuda"), torch.zeros(4, 768, device="cuda")
+    dpatch = torch.empty(3 * B * 128, 768, dtype=torch.bfloat16, device="cuda")
+    lib.call("edb_embed_assemble_bwd", g.data_ptr(), 3 * B, B, 128, cam.data_ptr(), 3.0, dpos.data_ptr(), dsie.data_ptr(),
+             dpatch.data_ptr(), lib.stream_ptr())
+    assert _rel(dpos, g.sum(0)) < 1e-5
+    want_sie = torch.zeros(4, 768, device="cuda").index_add_(0, cam.repeat(3), 3.0 * g.sum(1))
+    assert _rel(dsie, want_sie) < 1e-5
+    assert _rel(dpatch.float().view(3 * B, 128, 768), g[:, 1:]) < 1e-2
+
+
+def _torch_attention(qkv, lens, H=12):
+    outs, maps, off = [], [], 0
+    for L in lens:
+        blk = qkv[off:off + L].view(L, 3, H, 64).permute(1, 2, 0, 3)
+        q, k, v = blk[0], blk[1], blk[2]
+        a = ((q @ k.transpose(-2, -1)) * 0.125).softmax(-1)
+        outs.append((a @ v).transpose(0, 1).reshape(L, H * 64))
+        maps.append(a)
+        off += L
+    return torch.cat(outs, 0), maps
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("lens", [[129, 129, 129], [11, 83, 1, 62], [249, 33]])
+def test_attention_cuda_core_fwd_bwd(dtype, lens):
+    from editor_b200 import lib
+    T, H = sum(lens), 12
+    qkv32 = torch.randn(T, 3 * H * 64, generator=_g(1)).cuda()
+    qkv = qkv32.to(dtype)
+    seq_off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    ml = max(lens)
+    ldp = (ml + 7) // 8 * 8
+    out = torch.empty(T, H * 64, dtype=dtype, device="cuda")
+    P = torch.zeros(len(lens) * H, ml, ldp, dtype=dtype, device="cuda")
+    lib.attention(qkv, out, P, len(lens), H, ml, 0.125, seq_off=seq_off, p_rows=ml, ldp=ldp, impl=1)
+    qr = qkv.float().requires_grad_(True)
+    ref, maps = _torch_attention(qr, lens)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert _rel(out.float(), ref.detach()) < tol
+    for s, L in enumerate(lens):
+        got = P.view(len(lens), H, ml, ldp)[s, :, :L, :L].float()
+        assert _rel(got, maps[s].detach()) < tol
+    if dtype == torch.float32 and ml > 129:
+        return          # the fp32 backward is not a product path; its shared-memory tiles stop at 129 tokens
+    d_out = torch.randn(T, H * 64, generator=_g(2)).cuda().to(dtype)
+    ref.backward(d_out.float())
+    d_qkv = torch.empty_like(qkv)
+    lib.attention(qkv, None, P, len(lens), H, ml, 0.125, seq_off=seq_off, p_rows=ml, ldp=ldp, impl=1, d_out=d_out,
+                  d_qkv=d_qkv, backward=True)
+    assert _rel(d_qkv.float(), qr.grad) < (1e-4 if dtype == torch.float32 else 3e-2)
+
+
+def test_attention_tensor_core_matches_cuda_core():
+    """The tcgen05 kernel for 129-token sequences against the CUDA-core kernel and torch."""
+    from editor_b200 import lib
+    S, H = 7, 12
+    qkv = (torch.randn(S * 129, 2304, generator=_g(1)) * 1.5).cuda().to(torch.bfloat16)
+    outs, maps = [], []
+    for impl in (0, 1):
+        out = torch.zeros(S * 129, 768, dtype=torch.bfloat16, device="cuda")
+        P = torch.full((S * H, 129, 136), 7.0, dtype=torch.bfloat16, device="cuda")
+        lib.attention(qkv, out, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=impl)
+        outs.append(out)
+        maps.append(P)
+    torch.cuda.synchronize()
+    ref, rmaps = _torch_attention(qkv.float(), [129] * S)
+    assert _rel(outs[0].float(), ref) < 2e-2
+    assert _rel(outs[0].float(), outs[1].float()) < 2e-2
+    got = maps[0].view(S, H, 129, 136)
+    assert _rel(got[..., :129].float(), torch.stack(rmaps)) < 2e-2
+    assert torch.all(got[..., 129:] == 0)
+    d_out = torch.randn(S * 129, 768, generator=_g(2)).cuda().to(torch.bfloat16)
+    grads = []
+    for impl in (0, 1):
+        d_qkv = torch.zeros_like(qkv)
+        lib.attention(qkv, None, maps[1], S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=impl, d_out=d_out,
+                      d_qkv=d_qkv, backward=True)
+        grads.append(d_qkv)
+    torch.cuda.synchronize()
+    assert _rel(grads[0].float(), grads[1].float()) < 3e-2
+
+
+def test_selection_kernels_bit_exact():
+    from editor_b200 import lib, synth
+    for (H, W) in ((256, 128), (128, 256)):
+        x, _, _ = synth.synthetic_batch(6, H, W, seed=3)
+        xg = {k: v.cuda() for k, v in x.items()}
+        counts = torch.empty(6, 128, dtype=torch.int32, device="cuda")
+        lib.call("edb_freq_counts", xg["RGB"].data_ptr(), xg["NI"].data_ptr(), xg["TI"].data_ptr(), 6, H, W,
+                 counts.data_ptr(), lib.stream_ptr())
+        assert torch.equal(counts.cpu(), orc.frequency_counts(x["RGB"], x["NI"], x["TI"], faithful=True))
+    # top-k with heavy ties, every k, int and float rows -- against the rule measured on torch.topk (CUDA)
+    g = _g(5)
+    for k in (1, 2, 10, 16, 32, 64, 96, 128):
+        vi = torch.randint(100, 140, (64, 128), generator=g, dtype=torch.int32)
+        vi[0] = 256
+        vf = (torch.randint(0, 20, (64, 128), generator=g).float() / 16.0)
+        for vals, isf in ((vi, 0), (vf, 1)):
+            mask = torch.zeros(64, 4, dtype=torch.int32, device="cuda")
+            v = vals.cuda()
+            lib.call("edb_topk_mask", v.data_ptr(), isf, 128, 64, 128, k, mask.data_ptr(), 0, lib.stream_ptr())
+            bits = ((mask.cpu().view(-1, 4, 1) >> torch.arange(32).view(1, 1, 32)) & 1).bool().reshape(-1, 128)
+            assert torch.equal(bits, orc.topk_mask(vals, k)), k
+            idx = torch.topk(v, k, dim=1).indices
+            tm = torch.zeros(64, 128, dtype=torch.bool, device="cuda").scatter_(1, idx, True)
+            assert torch.equal(bits, tm.cpu()), ("torch.topk on this GPU", k)
+
+
+def test_rollout_topk_matches_oracle():
+    from editor_b200 import lib
+    B, S, H, L = 2, 6, 12, 12
+    maps = [torch.softmax(torch.randn(S, H, 129, 129, generator=_g(l)) * 2, -1) for l in range(L)]
+    bufs = []
+    for m in maps:
+        b = torch.zeros(S * H, 129, 136, device="cuda")
+        b[:, :, :129] = m.view(S * H, 129, 129).cuda()
+        bufs.append(b)
+    index = torch.zeros(B, 4, dtype=torch.int32, device="cuda")
+    mod = torch.zeros(S, 4, dtype=torch.int32, device="cuda")
+    rows = torch.empty(S * H, 128, device="cuda")
+    arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bufs])
+    lib.call("edb_rollout_topk", arr, L, 1, S, B, H, 129, 136, 2, index.data_ptr(), mod.data_ptr(), rows.data_ptr(),
+             lib.stream_ptr())
+    want_rows = orc.rollout_full(maps)                       # SFTS.py:150-153 as written (full matrix product)
+    assert _rel(rows.cpu().view(S, H, 128), want_rows) < 1e-4
+    want = orc.part_attention_mask(maps, 2, full=True)
+    bits = ((mod.cpu().view(-1, 4, 1) >> torch.arange(32).view(1, 1, 32)) & 1).bool().reshape(-1, 128)
+    assert torch.equal(bits, want)
+    ib = ((index.cpu().view(-1, 4, 1) >> torch.arange(32).view(1, 1, 32)) & 1).bool().reshape(-1, 128)
+    assert torch.equal(ib, want[0:2] | want[2:4] | want[4:6])
+
+
+def test_droppath_matches_oracle():
+    """DropPath (vit_pytorch.py:52-69) as per-sequence row scales in the residual epilogues and LN backward."""
+    import __graft_entry__ as ge
+    model, sd, x, label, cam, al = ge._small_case(True, 4)
+    model = model.cuda().train()
+    eng = model.engine()
+    g = _g(9)
+    dp = [torch.floor(0.7 + torch.rand(12, generator=g)) / 0.7 for _ in range(24)]
+    eng._droppath = lambda B, device: [d.to(device) for d in dp]
+    xg = {k: v.cuda() for k, v in x.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = model(xg, label=label.cuda(), cam_label=cam.cuda(), writer=None, epoch=1)
+    own_sel = ((eng.sel["index"].cpu().view(-1, 4, 1) >> torch.arange(32).view(1, 1, 32)) & 1).bool().reshape(-1, 128)
+    dpo = [[d[m * 4:(m + 1) * 4] for d in dp] for m in range(3)]
+    ref = orc.editor_forward(sd, x, cam, label=label, training=True, al=al, droppath=dpo, force_index=own_sel)
+    for a, b in zip(outs, ref):
+        assert _rel(a.float().cpu(), b.detach()) < 3e-2
