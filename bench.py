@@ -248,6 +248,19 @@ def main():
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "launches_per_step": len(tm), "gemm_ms_per_step": tt * 1e3,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)"}
+    breakdown = None
+    if rank == 0:
+        eng = model.engine()
+        eng.stats["events"] = []
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        trainer.step(xg, lg, cg)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record()
+        torch.cuda.synchronize()
+        ev = [("step_start", t0)] + eng.stats["events"] + [("step_end", t1)]
+        eng.stats["events"] = None
+        breakdown = {"%s->%s" % (a[0], b[0]): round(a[1].elapsed_time(b[1]), 3) for a, b in zip(ev[:-1], ev[1:])}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -271,7 +284,7 @@ def main():
             "step_tflops_of_peak": {"algorithmic_gflop_per_image": step_gflop_img,
                                     "achieved_tflops_per_gpu": step_gflop_img * B / ms_step,
                                     "frac_of_peak": step_gflop_img * B / ms_step / peak_s},
-            "roofline": roof, "loss": float(loss_host)}
+            "roofline": roof, "phase_ms": breakdown, "loss": float(loss_host)}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, t_step = cpu_oracle_rate(4, 2, 1, sd)

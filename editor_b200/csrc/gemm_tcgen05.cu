@@ -46,16 +46,100 @@ __device__ __forceinline__ float gelu_grad(float x) {
     return cdf + x * pdf;
 }
 
+// bf16-output epilogues: GELU and GELU' from MUFU-free odd minimax polynomials on the clamped argument
+// (Phi(x) - 1/2 and gelu'(x) - 1/2 as x*P(x^2), |x| <= 4; max abs error 2.7e-5 / 5.7e-4, below bf16 resolution).  The SFU
+// pipe issues 4 lanes/clk per sub-partition, so an ex2+rcp formulation costs more issue time than these 9 FMAs; the
+// fp32-output path (EDB_PREC_FP32) keeps exact erff.
+__device__ __forceinline__ float gelu_poly(float xc, const float (&c)[9]) {
+    const float t = xc * xc;
+    float p = c[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) p = fmaf(p, t, c[k]);
+    return fmaf(p, xc, 0.5f);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float c[9] = {3.989226805e-01f, -6.641063474e-02f, 9.877511128e-03f, -1.133936362e-03f, 9.891124782e-05f,
+                        -6.295397900e-06f, 2.716439822e-07f, -7.004532594e-09f, 8.065063692e-11f};
+    return x * gelu_poly(fminf(fmaxf(x, -4.0f), 4.0f), c);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    const float c[9] = {7.976096655e-01f, -2.648266008e-01f, 5.845612517e-02f, -8.716325173e-03f, 9.073272012e-04f,
+                        -6.495761995e-05f, 3.028349477e-06f, -8.218804372e-08f, 9.796053519e-10f};
+    return gelu_poly(fminf(fmaxf(x, -4.0f), 4.0f), c);
+}
+
+// kept out of line: the epilogue loop is fully unrolled (static register indexing of the prefetched aux operand) and
+// inlining the erf arithmetic 32 times would overflow the instruction cache
+__device__ __forceinline__ float4 gelu4_fast(float4 v) {
+    return make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w));
+}
+__device__ __forceinline__ float4 gelu_bwd4_fast(float4 v, uint2 pre) {
+    const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pre.x));
+    const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pre.y));
+    return make_float4(v.x * gelu_grad_fast(a0.x), v.y * gelu_grad_fast(a0.y), v.z * gelu_grad_fast(a1.x),
+                       v.w * gelu_grad_fast(a1.y));
+}
+__device__ __noinline__ float4 gelu4_exact(float4 v) {
+    return make_float4(gelu_exact(v.x), gelu_exact(v.y), gelu_exact(v.z), gelu_exact(v.w));
+}
+
 template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kStagingOffset = STAGES * kStageBytes;           // 8 epilogue warps x 4 KB transpose patches
+    static constexpr int kBarOffset = kStagingOffset + kNumEpiWarps * 4096;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+// 4 consecutive elements with a column predicate (nvalid = number of in-range columns, may exceed 4)
+__device__ __forceinline__ float4 ld4g(const float* p, int nvalid, bool vec) {
+    if (vec) return *reinterpret_cast<const float4*>(p);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = p[0];
+    if (nvalid > 1) v.y = p[1];
+    if (nvalid > 2) v.z = p[2];
+    if (nvalid > 3) v.w = p[3];
+    return v;
+}
+__device__ __forceinline__ float4 ld4g(const __nv_bfloat16* p, int nvalid, bool vec) {
+    if (vec) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = __bfloat162float(p[0]);
+    if (nvalid > 1) v.y = __bfloat162float(p[1]);
+    if (nvalid > 2) v.z = __bfloat162float(p[2]);
+    if (nvalid > 3) v.w = __bfloat162float(p[3]);
+    return v;
+}
+__device__ __forceinline__ void st4g(float* p, const float4& v, int nvalid, bool vec) {
+    if (vec) { *reinterpret_cast<float4*>(p) = v; return; }
+    p[0] = v.x;
+    if (nvalid > 1) p[1] = v.y;
+    if (nvalid > 2) p[2] = v.z;
+    if (nvalid > 3) p[3] = v.w;
+}
+__device__ __forceinline__ void st4g(__nv_bfloat16* p, const float4& v, int nvalid, bool vec) {
+    if (vec) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&lo);
+        u.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p) = u;
+        return;
+    }
+    p[0] = __float2bfloat16(v.x);
+    if (nvalid > 1) p[1] = __float2bfloat16(v.y);
+    if (nvalid > 2) p[2] = __float2bfloat16(v.z);
+    if (nvalid > 3) p[3] = __float2bfloat16(v.w);
+}
+
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
@@ -176,158 +260,136 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        // Each warp drains a 32-row x (BN/2)-column slab of the accumulator in 32-column chunks.  tcgen05.ld hands every
+        // lane one ROW; global memory wants lanes on consecutive COLUMNS.  So the chunk is transposed through a private
+        // 4 KB swizzled smem patch: phase A (row per lane) TMEM -> smem, phase B (8 lanes per row, 4 rows per access)
+        // smem -> bias / GELU / residual / GELU' -> fully coalesced 128-byte global accesses.  The aux operand of chunk
+        // c+1 (residual stream / saved pre-activation) is fetched while chunk c is processed.
         const int ew = warp - 4;
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-        const int half = ew >> 2;      // column half
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+        const int half = ew >> 2;              // column half
+        constexpr int NCH = BN / 64;           // 32-column chunks per warp
+        constexpr bool kAuxF32 = (EPI == EPI_RESIDUAL);
+        constexpr bool kAuxBf16 = (EPI == EPI_GELU_BWD);
+        uint8_t* stg = smem + S::kStagingOffset + ew * 4096;
+        const int lrow = lane >> 3;            // phase B: row within a group of 4
+        const int lc4 = lane & 7;              // phase B: which float4 of the 32-column chunk
         int acc = 0;
         uint32_t acc_phase = 0;
+        float4 axf_c[kAuxF32 ? 8 : 1], axf_n[kAuxF32 ? 8 : 1];     // fp32 aux: current / next chunk
+        uint2 axh_c[kAuxBf16 ? 8 : 1], axh_n[kAuxBf16 ? 8 : 1];     // bf16 aux
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             int tm, tn, ks;
             decode(w, tm, tn, ks);
+            const int row_base = tm * BM + quarter * 32;
+            const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            const int colw = tn * BN + half * (BN / 2) + lc4 * 4;
+            auto load_aux = [&](int c) {
+                const int col = colw + c * 32;
+                const int nvalid = p.N - col;
+                if (kAuxF32) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + it * 4 + lrow;
+                        axf_n[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < p.M && nvalid > 0)
+                            axf_n[it] = ld4g(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ld_aux + col, nvalid,
+                                             nvalid >= 4 && (p.ld_aux % 4 == 0));
+                    }
+                }
+                if (kAuxBf16) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + it * 4 + lrow;
+                        axh_n[it] = make_uint2(0u, 0u);
+                        if (row < p.M && nvalid > 0) {
+                            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ld_aux + col;
+                            if (nvalid >= 4 && (p.ld_aux % 4 == 0)) {
+                                axh_n[it] = *reinterpret_cast<const uint2*>(src);
+                            } else {
+                                unsigned short e[4] = {0, 0, 0, 0};
+                                for (int q = 0; q < 4; ++q)
+                                    if (q < nvalid) e[q] = *reinterpret_cast<const unsigned short*>(src + q);
+                                axh_n[it] = make_uint2((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16));
+                            }
+                        }
+                    }
+                }
+            };
+            load_aux(0);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = tm * BM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
-            const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 2; c += 32) {
-                const int col_t = half * (BN / 2) + c;
-                const int col0 = tn * BN + col_t;
+            for (int c = 0; c < NCH; ++c) {
+                const int col_t = half * (BN / 2) + c * 32;
+                const int col = colw + c * 32;                      // first of this lane's 4 columns in phase B
+                const int nvalid = p.N - col;                        // >= 4: all four columns exist
+                const bool vec = nvalid >= 4;
+                if (kAuxF32) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) axf_c[it] = axf_n[it];
+                }
+                if (kAuxBf16) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) axh_c[it] = axh_n[it];
+                }
+                // ---- phase A
                 uint32_t r[32];
                 tmem_ld_32x32(t_base + col_t, r);
+                if (c + 1 < NCH) load_aux(c + 1);
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr && EPI != EPI_ATOMIC && nvalid > 0) b4 = ld4g(p.bias + col, nvalid, vec);
                 tmem_ld_wait();
-                if (!row_ok || col0 >= p.N) continue;
-                float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-                const bool full = (col0 + 32 <= p.N);
-                if (p.bias != nullptr && p.epi != EPI_ATOMIC) {
-                    if (full) {
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                // ---- phase B
+                if (nvalid > 0) {
+                    const bool vD = vec && (p.ldd % 4 == 0), v2 = vec && (p.ld_out2 % 4 == 0);
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + lrow;
+                        const int row = row_base + rr;
+                        float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
+                        if (row >= p.M) continue;
+                        v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
+                        v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
+                        if (EPI == EPI_GELU) {
+                            if (p.out2 != nullptr) {
+                                if (p.out_f32) st4g(reinterpret_cast<float*>(p.out2) + (size_t)row * p.ld_out2 + col, v, nvalid, v2);
+                                else st4g(reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)row * p.ld_out2 + col, v, nvalid, v2);
+                            }
+                            v = p.out_f32 ? gelu4_exact(v) : gelu4_fast(v);
+                        } else if (EPI == EPI_RESIDUAL) {
+                            const float rsc = p.row_scale != nullptr ? p.row_scale[row / p.scale_group] : 1.0f;
+                            const float4 a = axf_c[kAuxF32 ? it : 0];
+                            v.x = fmaf(rsc, v.x, a.x); v.y = fmaf(rsc, v.y, a.y);
+                            v.z = fmaf(rsc, v.z, a.z); v.w = fmaf(rsc, v.w, a.w);
+                        } else if (EPI == EPI_GELU_BWD) {
+                            v = gelu_bwd4_fast(v, axh_c[kAuxBf16 ? it : 0]);
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
-                    }
-                }
-                if (p.epi == EPI_GELU) {
-                    if (p.out2 != nullptr) {
-                        if (p.out_f32) {
-                            float* o = reinterpret_cast<float*>(p.out2) + (size_t)row * p.ld_out2 + col0;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < p.N) o[i] = v[i];
-                        } else {
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)row * p.ld_out2 + col0;
-                            if (full) {
-#pragma unroll
-                                for (int i = 0; i < 32; i += 8) {
-                                    uint4 pk;
-                                    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                                    __nv_bfloat162 t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                                    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                                    __nv_bfloat162 t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                                    pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                                    pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                                    pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                                    pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                                    *reinterpret_cast<uint4*>(o + i) = pk;
-                                }
+                        if (EPI == EPI_ATOMIC) {
+                            float* o = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
+                            if (vD) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(o), "f"(v.x), "f"(v.y),
+                                             "f"(v.z), "f"(v.w)
+                                             : "memory");
                             } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (col0 + i < p.N) o[i] = __float2bfloat16(v[i]);
+                                atomicAdd(o, v.x);
+                                if (nvalid > 1) atomicAdd(o + 1, v.y);
+                                if (nvalid > 2) atomicAdd(o + 2, v.z);
+                                if (nvalid > 3) atomicAdd(o + 3, v.w);
                             }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_exact(v[i]);
-                } else if (p.epi == EPI_RESIDUAL) {
-                    const float* a = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ld_aux + col0;
-                    const float rsc = p.row_scale ? p.row_scale[row / p.scale_group] : 1.0f;
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(a + i);
-                            v[i] = a4.x + rsc * v[i]; v[i + 1] = a4.y + rsc * v[i + 1];
-                            v[i + 2] = a4.z + rsc * v[i + 2]; v[i + 3] = a4.w + rsc * v[i + 3];
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) v[i] = a[i] + rsc * v[i];
-                    }
-                } else if (p.epi == EPI_GELU_BWD) {
-                    if (p.aux_f32) {
-                        const float* a = reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ld_aux + col0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) v[i] *= gelu_grad(a[i]);
-                    } else {
-                        const __nv_bfloat16* a =
-                            reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ld_aux + col0;
-                        if (full) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                const uint4 pk = *reinterpret_cast<const uint4*>(a + i);
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 f = __bfloat1622float2(h[j]);
-                                    v[i + 2 * j] *= gelu_grad(f.x);
-                                    v[i + 2 * j + 1] *= gelu_grad(f.y);
-                                }
-                            }
+                        } else if (p.out_f32) {
+                            st4g(reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col, v, nvalid, vD);
                         } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < p.N) v[i] *= gelu_grad(__bfloat162float(a[i]));
+                            st4g(reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col, v, nvalid, vD);
                         }
                     }
                 }
-                // ---- store
-                if (p.epi == EPI_ATOMIC) {
-                    float* o = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (col0 + i < p.N) atomicAdd(o + i, v[i]);
-                } else if (p.out_f32) {
-                    float* o = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
-                    if (full && (p.ldd % 4 == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) o[i] = v[i];
-                    }
-                } else {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
-                    if (full && (p.ldd % 8 == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i], v[i + 1]);
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                            *reinterpret_cast<uint4*>(o + i) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.N) o[i] = __float2bfloat16(v[i]);
-                    }
-                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -387,19 +449,19 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, cudaStream_t stream) {
     using S = GemmSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             S::kTotal);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
         configured = true;
     }
     const int num_work = p.m_tiles * p.n_tiles * p.split_k;
     const int grid = num_work < num_sms() ? num_work : num_sms();
-    gemm_bf16_kernel<BN, STAGES><<<grid, kThreads, S::kTotal, stream>>>(ta, tb, p);
+    gemm_bf16_kernel<BN, STAGES, EPI><<<grid, kThreads, S::kTotal, stream>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
     return EDB_OK;
@@ -429,6 +491,8 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     p.row_scale = g.row_scale; p.scale_group = g.scale_group > 0 ? g.scale_group : 1;
     if (g.epilogue == EPI_RESIDUAL && (g.aux == nullptr || !g.aux_f32 || !g.out_f32))
         return edb_set_error(EDB_ERR_SHAPE, "gemm: the residual epilogue needs fp32 aux and fp32 output");
+    if (g.epilogue == EPI_GELU_BWD && (g.aux == nullptr || g.aux_f32))
+        return edb_set_error(EDB_ERR_SHAPE, "gemm: the GELU-backward epilogue needs the bf16 pre-activation as aux");
 
     CUtensorMap ta, tb;
     int rc;
@@ -438,8 +502,20 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     if (!g.b_mn_major) rc = make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN);
     else               rc = make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BK);
     if (rc != EDB_OK) return rc;
-    if (BN == 256) return launch_gemm<256, 4>(ta, tb, p, stream);
-    return launch_gemm<128, 6>(ta, tb, p, stream);
+#define EDB_LAUNCH_EPI(E)                                             \
+    case E:                                                           \
+        if (BN == 256) return launch_gemm<256, 4, E>(ta, tb, p, stream); \
+        return launch_gemm<128, 6, E>(ta, tb, p, stream);
+    switch (g.epilogue) {
+        EDB_LAUNCH_EPI(EPI_STORE)
+        EDB_LAUNCH_EPI(EPI_GELU)
+        EDB_LAUNCH_EPI(EPI_RESIDUAL)
+        EDB_LAUNCH_EPI(EPI_GELU_BWD)
+        EDB_LAUNCH_EPI(EPI_ATOMIC)
+        default:
+            return edb_set_error(EDB_ERR_UNSUPPORTED, "gemm: unknown epilogue");
+    }
+#undef EDB_LAUNCH_EPI
 }
 
 }  // namespace edb

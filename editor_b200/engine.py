@@ -203,6 +203,13 @@ class EditorEngine:
         self.bb_plist = [self.arena.params[self.arena.names.index(n)] for n in self.bb_names]
         self.hma_plist = [self.arena.params[self.arena.names.index(n)] for n in self.hma_names]
 
+    def _mark(self, name):
+        ev = self.stats.get("events")
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
     # ------------------------------------------------------------------ building blocks
     def _linear(self, x, L, out, rows, prec, epi=lib.EPI_STORE, aux=None, out2=None, row_scale=None, group=1):
         if prec == BF16:
@@ -472,16 +479,10 @@ class EditorEngine:
         rates = self.model.BACKBONE.base.drop_path_rates
         if max(rates) <= 0.0:
             return None
-        out = [torch.ones(3 * B, dtype=torch.float32, device=device) for _ in range(24)]
-        for m in range(3):
-            for l, r in enumerate(rates):
-                if r <= 0.0:
-                    continue
-                keep = 1.0 - r
-                for j in range(2):
-                    rnd = torch.rand((B,), dtype=torch.float32, device=device)
-                    out[2 * l + j][m * B:(m + 1) * B] = torch.floor(keep + rnd) / keep
-        return out
+        keep = 1.0 - torch.tensor(rates, dtype=torch.float32, device=device).repeat_interleave(2).unsqueeze(1)  # [24,1]
+        rnd = torch.rand((24, 3 * B), dtype=torch.float32, device=device)     # one draw for the whole step
+        scales = torch.floor(keep + rnd) / keep                               # keep_prob + rand, floor, / keep_prob
+        return list(scales.unbind(0))
 
     def forward(self, x, cam_label, label, writer, epoch):
         m = self.model
@@ -561,15 +562,20 @@ class EditorEngine:
 class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, rgb, ni, ti, cam, prec, dp, *params):
+        eng._mark("bb_fwd_start")
         tokens, sv = eng.backbone_forward(rgb, ni, ti, cam, prec, keep=True, droppath=dp)
+        eng._mark("bb_fwd_end")
         eng.sel = eng.select(rgb, ni, ti, sv["maps"], prec, want_debug=eng.stats.get("debug", False))
+        eng._mark("select_end")
         ctx.eng, ctx.sv, ctx.nparams = eng, sv, len(params)
         return tokens
 
     @staticmethod
     def backward(ctx, d_tokens):
         eng = ctx.eng
+        eng._mark("bb_bwd_start")
         eng.backbone_backward(ctx.sv, d_tokens.contiguous().float())
+        eng._mark("bb_bwd_end")
         eng.arena.attach_grads(set(eng.bb_names))
         return (None,) * (7 + ctx.nparams)
 
@@ -577,7 +583,9 @@ class _BackboneFn(torch.autograd.Function):
 class _HMAFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, tokens, prec, *params):
+        eng._mark("hma_fwd_start")
         cls_out, patch_mean, cls_mid, loss_bcc, num, sv = eng.hma_forward(tokens, eng.sel, prec, True)
+        eng._mark("hma_fwd_end")
         eng.last = dict(num=num, tokens=tokens)
         ctx.eng, ctx.sv, ctx.sel, ctx.nparams = eng, sv, eng.sel, len(params)
         ctx.save_for_backward(tokens)
@@ -589,8 +597,10 @@ class _HMAFn(torch.autograd.Function):
         (tokens,) = ctx.saved_tensors
         z = lambda t, ref: torch.zeros_like(ref) if t is None else t.contiguous().float()   # noqa: E731
         shape_ref = torch.empty(3, ctx.sel["B"], DIM, device=tokens.device)
+        eng._mark("hma_bwd_start")
         d_tokens = eng.hma_backward(tokens, ctx.sel, ctx.sv, z(d_cls, shape_ref), z(d_patch, shape_ref),
                                     None if d_mid is None else d_mid.contiguous().float(),
                                     None if d_bcc is None else d_bcc.contiguous().float())
+        eng._mark("hma_bwd_end")
         eng.arena.attach_grads(set(eng.hma_names))
         return (None, d_tokens, None) + (None,) * ctx.nparams
