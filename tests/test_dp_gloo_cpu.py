@@ -1,0 +1,95 @@
+"""Data-parallel host logic on CPU (gloo, world_size 2): flat-arena gradient allreduce + the optimizer arithmetic of
+edb_sgd_step must equal the reference recipe -- per-rank backward, gradient average (DDP), torch.optim.SGD with the
+reference's parameter groups (solver/make_optimizer.py:6-22)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sgd_oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _build(seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [("blocks.0.attn.qkv.weight", (96, 32)), ("blocks.0.attn.qkv.bias", (96,)), ("norm.weight", (32,)),
+              ("norm.bias", (32,)), ("base.fc.weight", (10, 32)), ("head.weight", (7, 32))]
+    return [(n, torch.randn(s, generator=g)) for n, s in shapes]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = _build(0)                                  # replicated parameters
+    grads = [[g for _, g in _build(100 + rank + 10 * step)] for step in range(3)]     # per-rank gradients, 3 steps
+    # ---- flat arena exactly as engine.Arena / train.Trainer lay it out
+    offs, off = {}, 0
+    for n, p in params:
+        offs[n] = (off, p.numel())
+        off += (p.numel() + 63) // 64 * 64
+    flat, buf = torch.zeros(off), torch.zeros(off)
+    flags = torch.full((off // 64,), 2, dtype=torch.uint8)
+    for n, p in params:
+        o, k = offs[n]
+        flat[o:o + k] = p.flatten()
+        flags[o // 64:(o + k + 63) // 64] = 2 if n.startswith("base.fc.") else (1 if "bias" in n else 0)
+    for step in range(3):
+        garena = torch.zeros(off)
+        for (n, _), g in zip(params, grads[step]):
+            o, k = offs[n]
+            garena[o:o + k] = g.flatten()
+        dist.all_reduce(garena, op=dist.ReduceOp.SUM)      # the one collective of the path
+        sgd_oracle.flat_sgd_step(flat, garena, buf, flags, 0.001, 0.9, 1e-4, 1e-4, 2.0, 1.0 / world, step == 0)
+    if rank == 0:
+        torch.save({"flat": flat, "offs": offs}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_sgd_matches_reference_recipe(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    # reference recipe on one process: average the per-rank gradients, reference optimizer groups
+    named = [(n, torch.nn.Parameter(p.clone(), requires_grad=not n.startswith("base.fc."))) for n, p in _build(0)]
+    opt = sgd_oracle.reference_optimizer(named)
+    for step in range(3):
+        per_rank = [[g for _, g in _build(100 + r + 10 * step)] for r in range(world)]
+        for i, (n, p) in enumerate(named):
+            if p.requires_grad:
+                p.grad = sum(per_rank[r][i] for r in range(world)) / world
+        opt.step()
+    for n, p in named:
+        o, k = got["offs"][n]
+        assert torch.allclose(got["flat"][o:o + k].view(p.shape), p.detach(), rtol=1e-6, atol=1e-7), n
+
+
+def test_trainer_flags_follow_reference_groups():
+    """train.Trainer marks bias chunks (lr x2), skips the never-used BACKBONE.base.fc.* and the alignment padding."""
+    from editor_b200.train import Trainer
+
+    class FakeArena:
+        pass
+    a = FakeArena()
+    a.names = ["BACKBONE.base.blocks.0.attn.qkv.weight", "BACKBONE.base.blocks.0.attn.qkv.bias", "BACKBONE.base.fc.weight",
+               "FUSE_HEAD.weight"]
+    a.offsets = {a.names[0]: (0, 100, (100,)), a.names[1]: (128, 10, (10,)), a.names[2]: (192, 64, (64,)),
+                 a.names[3]: (256, 65, (65,))}
+    a.total = 384
+    a.flat = torch.zeros(a.total)
+    a.params = [torch.nn.Parameter(torch.zeros(1)) for _ in a.names]
+    t = Trainer(torch.nn.Linear(1, 1))
+    t._setup(a)
+    assert t.flags.tolist() == [0, 0, 1, 2, 0, 0]
+    assert [n for n, _ in t.tail] == ["FUSE_HEAD.weight"]

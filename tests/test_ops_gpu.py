@@ -251,3 +251,22 @@ def test_droppath_matches_oracle():
     ref = orc.editor_forward(sd, x, cam, label=label, training=True, al=al, droppath=dpo, force_index=own_sel)
     for a, b in zip(outs, ref):
         assert _rel(a.float().cpu(), b.detach()) < 3e-2
+
+
+def test_sgd_kernel_matches_reference_optimizer_arithmetic():
+    from editor_b200 import lib
+    from oracle import sgd_oracle
+    n = 64 * 50
+    g = _g(3)
+    p0, gr = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    flags = torch.randint(0, 3, (n // 64,), generator=g, dtype=torch.uint8)
+    pc, bc = p0.clone(), torch.zeros(n)
+    pg, bg, p16 = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    for step in range(3):
+        grs = gr * (step + 1)
+        sgd_oracle.flat_sgd_step(pc, grs, bc, flags, 0.001, 0.9, 1e-4, 1e-4, 2.0, 0.5, step == 0)
+        lib.call("edb_sgd_step", pg.data_ptr(), grs.cuda().data_ptr(), bg.data_ptr(), p16.data_ptr(), flags.cuda().data_ptr(),
+                 n, 0.001, 0.9, 1e-4, 1e-4, 2.0, 0.5, int(step == 0), lib.stream_ptr())
+    assert torch.allclose(pg.cpu(), pc, rtol=1e-6, atol=1e-7)
+    live = (flags.repeat_interleave(64) & 2) == 0
+    assert torch.equal(p16.cpu()[live], pc.to(torch.bfloat16)[live])
