@@ -64,11 +64,13 @@ static bool tc_eligible(const EdbAttnDesc* d) {
 }
 int edb_attention_fwd(const EdbAttnDesc* d, void* stream) {
     if (d == nullptr) return edb::edb_set_error(EDB_ERR_SHAPE, "null descriptor");
+    if (d->impl == 2) return edb::attention_var(*d, false, ST);
     if (tc_eligible(d)) return edb::attention_tc_fwd(*d, ST);
     return edb::attention_simple(*d, false, ST);
 }
 int edb_attention_bwd(const EdbAttnDesc* d, void* stream) {
     if (d == nullptr) return edb::edb_set_error(EDB_ERR_SHAPE, "null descriptor");
+    if (d->impl == 2) return edb::attention_var(*d, true, ST);
     if (tc_eligible(d)) return edb::attention_tc_bwd(*d, ST);
     return edb::attention_simple(*d, true, ST);
 }

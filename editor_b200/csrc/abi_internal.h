@@ -45,6 +45,7 @@ int embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam
 int sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr, float mu,
              float wd, float wd_bias, float bias_lr_factor, float gscale, int first, cudaStream_t st);
 int attention_simple(const EdbAttnDesc& d, bool bwd, cudaStream_t st);
+int attention_var(const EdbAttnDesc& d, bool bwd, cudaStream_t st);
 int attention_tc_fwd(const EdbAttnDesc& d, cudaStream_t st);
 int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st);
 int freq_counts(const float* rgb, const float* ni, const float* ti, int B, int H, int W, int* counts, cudaStream_t st);

@@ -384,19 +384,29 @@ class EditorEngine:
         return sel
 
     # ------------------------------------------------------------------ HMA on packed kept tokens
-    def _varlen_attn(self, seq_off, nseq, max_len, tagP, prec):
+    def _varlen_attn(self, seq_off, nseq, max_len, tagP, prec, total_rows):
+        """AttentionMask on packed kept tokens: tensor-core var-len kernel (bf16, <= 256 tokens) or the CUDA-core kernel
+        (fp32-faithful mode, or sequences whose padded key count does not fit the tensor-core tiles)."""
         ws = self.ws
-        ldp = _align(max_len, 8)
+        use_tc = prec == BF16 and max_len <= 256 and self.stats.get("hma_attn_impl", 2) == 2
+        if use_tc:
+            kp = 128 if max_len <= 128 else 256
+            p_rows, ldp, impl = (max_len + 127) // 128 * 128, kp, 2
+        else:
+            if max_len > 256:
+                raise lib.EdbError("HMA sequences longer than 256 kept tokens are not supported (got %d)" % max_len)
+            p_rows, ldp, impl = max_len, _align(max_len, 8), 1
         pdt = torch.bfloat16 if prec == BF16 else torch.float32
 
         def fwd(qkv, out, tag):
-            Pm = ws.get(tagP + tag, (nseq * HEADS, max_len, ldp), pdt)
-            lib.attention(qkv, out, Pm, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=max_len, ldp=ldp, impl=1)
+            Pm = ws.get(tagP + tag, (nseq * HEADS, p_rows, ldp), pdt)
+            lib.attention(qkv, out, Pm, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=p_rows, ldp=ldp, impl=impl,
+                          total_rows=total_rows)
             return Pm
 
         def bwd(qkv, P, datt, dqkv):
-            lib.attention(qkv, None, P, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=max_len, ldp=ldp, impl=1,
-                          d_out=datt, d_qkv=dqkv, backward=True)
+            lib.attention(qkv, None, P, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=p_rows, ldp=ldp, impl=impl,
+                          d_out=datt, d_qkv=dqkv, backward=True, total_rows=total_rows)
         return fwd, bwd
 
     def hma_forward(self, tokens, sel, prec, training):
@@ -410,7 +420,7 @@ class EditorEngine:
         loss_bcc = torch.zeros(1, dtype=torch.float32, device=dev) if training else None
         lib.call("edb_sfts_pack_fwd", tokens.data_ptr(), sel["index"].data_ptr(), sel["seq_off"].data_ptr(), B, cap,
                  xp.data_ptr(), lib.ptr(loss_bcc), lib.stream_ptr())
-        afwd, abwd = self._varlen_attn(sel["seq_off"], B, ml, "hmaP", prec)
+        afwd, abwd = self._varlen_attn(sel["seq_off"], B, ml, "hmaP", prec, T)
         x2all = ws.get("hma_x2", (3, cap, DIM), torch.float32)
         x1all = ws.get("hma_x1", (3, cap, DIM), torch.float32)
         saved = []
@@ -424,7 +434,7 @@ class EditorEngine:
         xj = ws.get("hma_xj", (3 * cap, DIM), torch.float32)
         lib.call("edb_joint_gather", x2all.data_ptr(), cap, xj.data_ptr(), sel["seq_off"].data_ptr(), B, ml, 0,
                  lib.stream_ptr())
-        jfwd, jbwd = self._varlen_attn(sel["seq_off3"], B, 3 * ml, "hmaPj", prec)
+        jfwd, jbwd = self._varlen_attn(sel["seq_off3"], B, 3 * ml, "hmaPj", prec, 3 * T)
         xj1 = ws.get("hma_xj1", (3 * cap, DIM), torch.float32)
         xj2 = ws.get("hma_xj2", (3 * cap, DIM), torch.float32)
         svj = self._block_fwd(xj, xj1, xj2, 3 * T, self.hma_blocks[3], jfwd, "hmaJ_", prec)

@@ -47,6 +47,7 @@ class AttnDesc(ctypes.Structure):
         ("impl", c_int),
         ("d_out", c_vp), ("ld_dout", c_ll),
         ("d_qkv", c_vp),
+        ("total_rows", c_ll),
     ]
 
 
@@ -198,7 +199,7 @@ def split3(src, dst, role, rows=None):
 
 
 def attention(qkv, out, P, nseq, heads, max_len, scale, seq_off=None, fixed_len=0, p_rows=0, ldp=0, impl=0,
-              d_out=None, d_qkv=None, backward=False):
+              d_out=None, d_qkv=None, backward=False, total_rows=0):
     d = AttnDesc()
     d.qkv, d.ld_qkv = qkv.data_ptr(), qkv.stride(0)
     if out is not None:
@@ -206,6 +207,7 @@ def attention(qkv, out, P, nseq, heads, max_len, scale, seq_off=None, fixed_len=
     d.P, d.p_rows, d.ldp = ptr(P), p_rows, ldp
     d.seq_off, d.fixed_len, d.nseq, d.heads, d.max_len = ptr(seq_off), fixed_len, nseq, heads, max_len
     d.scale, d.f32, d.impl = scale, _f32(qkv), impl
+    d.total_rows = total_rows
     if backward:
         d.d_out, d.ld_dout, d.d_qkv = d_out.data_ptr(), d_out.stride(0), d_qkv.data_ptr()
     call("edb_attention_bwd" if backward else "edb_attention_fwd", ctypes.byref(d), stream_ptr())

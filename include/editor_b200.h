@@ -118,7 +118,9 @@ int edb_embed_assemble_bwd(const float* g, int S, int B, int P, const long long*
 /* softmax(q k^T * scale) v per (sequence, head) on a packed [rows][3*heads*64] qkv matrix; optionally stores the
  * post-softmax maps P (the reference returns them, vit_pytorch.py:195-196; SFTS consumes them, SFTS.py:145-153).
  * Sequences: seq_off (nseq+1 int32 row offsets, device) or fixed_len.  impl: 0 = tensor-core kernel when the shape
- * allows (bf16, fixed_len 129), 1 = CUDA-core kernel (any length <= 256, fp32 or bf16 storage).
+ * allows (bf16, fixed_len 129), 1 = CUDA-core kernel (any length <= 256, fp32 or bf16 storage), 2 = tensor-core
+ * kernel for packed var-len sequences (bf16, length <= 256, P stored as [ceil(max_len/128)*128][ldp] blocks with
+ * ldp = 128 or 256, zero outside the sequence).
  * Also serves AttentionMask (vit_pytorch.py:240-258) on packed kept tokens. */
 typedef struct EdbAttnDesc {
     const void* qkv; long long ld_qkv;
@@ -130,6 +132,7 @@ typedef struct EdbAttnDesc {
     int impl;
     const void* d_out; long long ld_dout;   /* backward */
     void* d_qkv;                            /* backward, same pitch as qkv */
+    long long total_rows;                   /* impl 2: rows of the packed qkv / out matrices */
 } EdbAttnDesc;
 int edb_attention_fwd(const EdbAttnDesc* desc, void* stream);
 int edb_attention_bwd(const EdbAttnDesc* desc, void* stream);

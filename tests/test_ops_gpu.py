@@ -270,3 +270,59 @@ def test_sgd_kernel_matches_reference_optimizer_arithmetic():
     assert torch.allclose(pg.cpu(), pc, rtol=1e-6, atol=1e-7)
     live = (flags.repeat_interleave(64) & 2) == 0
     assert torch.equal(p16.cpu()[live], pc.to(torch.bfloat16)[live])
+
+
+@pytest.mark.parametrize("lens", [[11, 83, 1, 62, 128], [249, 33, 130, 256, 7]])
+def test_attention_tensor_core_varlen(lens):
+    """tcgen05 var-len kernel (impl 2, HMA's packed AttentionMask) against torch and the CUDA-core kernel."""
+    from editor_b200 import lib
+    T, H = sum(lens), 12
+    qkv = (torch.randn(T, 3 * H * 64, generator=_g(1)) * 1.2).cuda().to(torch.bfloat16)
+    seq_off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    ml = max(lens)
+    kp = 128 if ml <= 128 else 256
+    pr = (ml + 127) // 128 * 128
+    out = torch.zeros(T, H * 64, dtype=torch.bfloat16, device="cuda")
+    P = torch.full((len(lens) * H, pr, kp), 3.0, dtype=torch.bfloat16, device="cuda")
+    lib.attention(qkv, out, P, len(lens), H, ml, 0.125, seq_off=seq_off, p_rows=pr, ldp=kp, impl=2, total_rows=T)
+    torch.cuda.synchronize()
+    qr = qkv.float().requires_grad_(True)
+    ref, maps = _torch_attention(qr, lens)
+    assert _rel(out.float(), ref.detach()) < 2e-2
+    Pv = P.view(len(lens), H, pr, kp)
+    for s, L in enumerate(lens):
+        assert _rel(Pv[s, :, :L, :L].float(), maps[s].detach()) < 2e-2
+        nq = (L + 127) // 128 * 128
+        assert torch.all(Pv[s, :, :nq, L:] == 0) and torch.all(Pv[s, :, L:nq, :] == 0)     # zero outside the sequence
+    d_out = torch.randn(T, H * 64, generator=_g(2)).cuda().to(torch.bfloat16)
+    ref.backward(d_out.float())
+    d_qkv = torch.zeros_like(qkv)
+    lib.attention(qkv, None, P, len(lens), H, ml, 0.125, seq_off=seq_off, p_rows=pr, ldp=kp, impl=2, d_out=d_out,
+                  d_qkv=d_qkv, backward=True, total_rows=T)
+    torch.cuda.synchronize()
+    assert _rel(d_qkv.float(), qr.grad) < 3e-2
+
+
+def test_rollout_topk_bf16_maps():
+    from editor_b200 import lib
+    B, S, H, L = 2, 6, 12, 12
+    maps = [torch.softmax(torch.randn(S, H, 129, 129, generator=_g(20 + l)) * 2, -1).to(torch.bfloat16) for l in range(L)]
+    bufs = []
+    for m in maps:
+        b = torch.zeros(S * H, 129, 136, dtype=torch.bfloat16, device="cuda")
+        b[:, :, :129] = m.view(S * H, 129, 129).cuda()
+        bufs.append(b)
+    index = torch.zeros(B, 4, dtype=torch.int32, device="cuda")
+    mod = torch.zeros(S, 4, dtype=torch.int32, device="cuda")
+    rows = torch.empty(S * H, 128, device="cuda")
+    arr = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bufs])
+    lib.call("edb_rollout_topk", arr, L, 0, S, B, H, 129, 136, 2, index.data_ptr(), mod.data_ptr(), rows.data_ptr(),
+             lib.stream_ptr())
+    mf = [m.float() for m in maps]
+    want_rows = orc.rollout_cls_row(mf)
+    assert _rel(rows.cpu().view(S, H, 128), want_rows) < 1e-4
+    got = ((mod.cpu().view(-1, 4, 1) >> torch.arange(32).view(1, 1, 32)) & 1).bool().reshape(-1, 128)
+    kth = torch.sort(want_rows, dim=-1, descending=True).values
+    safe = ((kth[..., 1] - kth[..., 2]) / kth[..., 1] > 1e-3).all(1)     # rows whose top-2 is not a near-tie
+    want = orc.part_attention_mask(mf, 2)
+    assert safe.sum() >= S - 1 and torch.equal(got[safe], want[safe])
