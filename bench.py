@@ -230,12 +230,13 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in xh.values()) + lh.numel() * 8 + ch.numel() * 8
     # ---- dominant kernel (tcgen05 GEMM): per-launch CUDA-event timing over one extra step, outside the timed region
     roof = None
+    # (every rank runs the two extra, untimed steps below: the step contains the gradient allreduce)
+    lib.gemm_timing = []
+    trainer.step(xg, lg, cg)
+    torch.cuda.synchronize()
+    tm = lib.gemm_timing
+    lib.gemm_timing = None
     if rank == 0:
-        lib.gemm_timing = []
-        trainer.step(xg, lg, cg)
-        torch.cuda.synchronize()
-        tm = lib.gemm_timing
-        lib.gemm_timing = None
         fl = sum(f for f, _, _ in tm)
         tt = sum(a.elapsed_time(b) for _, a, b in tm) * 1e-3
         peaks = {}
@@ -245,22 +246,27 @@ def main():
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = fl / tt / 1e12 if tt > 0 else 0.0
+        traffic = None
+        try:        # dram bytes per launch from the committed ncu --set full capture of this kernel (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))["mean_dram_bytes_per_launch"]
+        except (OSError, KeyError):
+            pass
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "launches_per_step": len(tm), "gemm_ms_per_step": tt * 1e3,
+                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch_mean": None,
+                "launches_per_step": len(tm), "gemm_ms_per_step": tt * 1e3,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)"}
-    breakdown = None
-    if rank == 0:
-        eng = model.engine()
-        eng.stats["events"] = []
-        t0 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        trainer.step(xg, lg, cg)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t1.record()
-        torch.cuda.synchronize()
-        ev = [("step_start", t0)] + eng.stats["events"] + [("step_end", t1)]
-        eng.stats["events"] = None
-        breakdown = {"%s->%s" % (a[0], b[0]): round(a[1].elapsed_time(b[1]), 3) for a, b in zip(ev[:-1], ev[1:])}
+    eng = model.engine()
+    eng.stats["events"] = []
+    t0 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    trainer.step(xg, lg, cg)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ev = [("step_start", t0)] + eng.stats["events"] + [("step_end", t1)]
+    eng.stats["events"] = None
+    breakdown = {"%s->%s" % (a[0], b[0]): round(a[1].elapsed_time(b[1]), 3) for a, b in zip(ev[:-1], ev[1:])}
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
