@@ -24,21 +24,29 @@ int edb_gemm_bf16(const EdbGemmDesc* d, void* stream) {
 #define ST static_cast<cudaStream_t>(stream)
 
 int edb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
-                      long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, void* stream) {
-    return edb::layernorm_fwd(x, ldx, gamma, beta, eps, y, ldy, y_f32, mean, rstd, rows, dim, ST);
+                      long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, const int* rows_dev,
+                      void* stream) {
+    return edb::layernorm_fwd(x, ldx, gamma, beta, eps, y, ldy, y_f32, mean, rstd, rows, dim, rows_dev, ST);
 }
 size_t edb_layernorm_bwd_workspace_bytes(void) { return edb::layernorm_bwd_workspace_bytes(); }
 int edb_layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
                       const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg,
                       void* g_bf16, long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace,
-                      size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, void* stream) {
+                      size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, const int* rows_dev,
+                      void* stream) {
     return edb::layernorm_bwd(dy, lddy, dy_f32, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, g_bf16, ldgb, dgamma, dbeta,
-                              dcol, workspace, ws_bytes, rows, dim, row_scale, scale_group, ST);
+                              dcol, workspace, ws_bytes, rows, dim, row_scale, scale_group, rows_dev, ST);
 }
 int edb_colsum(const void* src, long long ld, int src_f32, int rows, int n, float* out, void* stream) {
     return edb::colsum(src, ld, src_f32, rows, n, out, ST);
 }
 int edb_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream) { return edb::cast_f32_bf16(src, dst, n, ST); }
+int edb_cast_rows_f32_bf16(const float* src, void* dst, int max_rows, int cols, const int* rows_dev, void* stream) {
+    return edb::cast_rows_f32_bf16(src, dst, max_rows, cols, rows_dev, ST);
+}
+int edb_zero_rows(void* base, long long row_bytes, const int* rows_dev, int nrows, void* stream) {
+    return edb::zero_rows(base, row_bytes, rows_dev, nrows, ST);
+}
 int edb_sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr,
                  float momentum, float wd, float wd_bias, float bias_lr_factor, float gscale, int first, void* stream) {
     return edb::sgd_step(p, g, buf, p16, flags, n, lr, momentum, wd, wd_bias, bias_lr_factor, gscale, first, ST);

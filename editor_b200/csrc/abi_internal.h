@@ -27,14 +27,17 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, long long inner, long lon
 int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream);
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
-                  long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, cudaStream_t st);
+                  long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, const int* rows_dev,
+                  cudaStream_t st);
 size_t layernorm_bwd_workspace_bytes();
 int layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
                   const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg, void* g_bf16,
                   long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace, size_t ws_bytes, int rows,
-                  int dim, const float* row_scale, int scale_group, cudaStream_t st);
+                  int dim, const float* row_scale, int scale_group, const int* rows_dev, cudaStream_t st);
 int colsum(const void* src, long long ld, int src_f32, int rows, int N, float* out, cudaStream_t st);
 int cast_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
+int cast_rows_f32_bf16(const float* src, void* dst, int max_rows, int cols, const int* rows_dev, cudaStream_t st);
+int zero_rows(void* base, long long row_bytes, const int* rows_dev, int nrows, cudaStream_t st);
 int split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, cudaStream_t st);
 int patch_im2col(const float* rgb, const float* ni, const float* ti, int B, int H, int W, void* out, long long ldo,
                  int out_f32, cudaStream_t st);

@@ -37,6 +37,8 @@ struct GemmKernelParams {
     float alpha;
     const float* row_scale;
     int scale_group;
+    const int* M_dev;   // optional: number of valid rows read on the device (packed HMA rows; no host sync)
+    const int* K_dev;   // optional: reduction length read on the device (wgrad over packed rows)
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -176,7 +178,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int num_work = p.m_tiles * p.n_tiles * p.split_k;
+    const int M_rt = p.M_dev != nullptr ? *p.M_dev : p.M;
+    const int m_tiles = (M_rt + BM - 1) / BM;
+    int kb_total = p.kb_total, kb_per_split = p.kb_per_split;
+    if (p.K_dev != nullptr) {
+        kb_total = (*p.K_dev + BK - 1) / BK;
+        kb_per_split = (kb_total + p.split_k - 1) / p.split_k;
+    }
+    const int num_work = m_tiles * p.n_tiles * p.split_k;
     constexpr int GM = 16;  // m-tiles per raster group (keeps the group's A tiles + all of B resident in L2)
 
     auto decode = [&](int w, int& tm, int& tn, int& ks) {
@@ -185,7 +194,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int per_group = GM * p.n_tiles;
         const int g = t / per_group;
         const int within = t - g * per_group;
-        const int gsize = min(GM, p.m_tiles - g * GM);
+        const int gsize = min(GM, m_tiles - g * GM);
         tm = g * GM + within % gsize;
         tn = within / gsize;
     };
@@ -198,8 +207,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 int tm, tn, ks;
                 decode(w, tm, tn, ks);
-                const int kb0 = ks * p.kb_per_split;
-                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int kb0 = ks * kb_per_split;
+                const int kb1 = min(kb_total, kb0 + kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::kStageBytes;
@@ -235,8 +244,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
                 int tm, tn, ks;
                 decode(w, tm, tn, ks);
-                const int kb0 = ks * p.kb_per_split;
-                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int kb0 = ks * kb_per_split;
+                const int kb1 = min(kb_total, kb0 + kb_per_split);
+                if (kb0 >= kb1) continue;      // empty split (device-side K shorter than the host bound)
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -281,6 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             int tm, tn, ks;
             decode(w, tm, tn, ks);
+            if (ks * kb_per_split >= kb_total) continue;      // empty split: the issuer skipped it too
             const int row_base = tm * BM + quarter * 32;
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
             const int colw = tn * BN + half * (BN / 2) + lc4 * 4;
@@ -292,7 +303,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int it = 0; it < 8; ++it) {
                         const int row = row_base + it * 4 + lrow;
                         axf_n[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row < p.M && nvalid > 0)
+                        if (row < M_rt && nvalid > 0)
                             axf_n[it] = ld4g(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ld_aux + col, nvalid,
                                              nvalid >= 4 && (p.ld_aux % 4 == 0));
                     }
@@ -302,7 +313,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int it = 0; it < 8; ++it) {
                         const int row = row_base + it * 4 + lrow;
                         axh_n[it] = make_uint2(0u, 0u);
-                        if (row < p.M && nvalid > 0) {
+                        if (row < M_rt && nvalid > 0) {
                             const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ld_aux + col;
                             if (nvalid >= 4 && (p.ld_aux % 4 == 0)) {
                                 axh_n[it] = *reinterpret_cast<const uint2*>(src);
@@ -353,7 +364,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const int rr = it * 4 + lrow;
                         const int row = row_base + rr;
                         float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
-                        if (row >= p.M) continue;
+                        if (row >= M_rt) continue;
                         v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
                         v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
                         if (EPI == EPI_GELU) {
@@ -489,6 +500,7 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     p.bias = g.bias; p.aux = g.aux; p.ld_aux = g.ld_aux; p.aux_f32 = g.aux_f32;
     p.out2 = g.out2; p.ld_out2 = g.ld_out2; p.alpha = g.alpha;
     p.row_scale = g.row_scale; p.scale_group = g.scale_group > 0 ? g.scale_group : 1;
+    p.M_dev = g.M_dev; p.K_dev = g.K_dev;
     if (g.epilogue == EPI_RESIDUAL && (g.aux == nullptr || !g.aux_f32 || !g.out_f32))
         return edb_set_error(EDB_ERR_SHAPE, "gemm: the residual epilogue needs fp32 aux and fp32 output");
     if (g.epilogue == EPI_GELU_BWD && (g.aux == nullptr || g.aux_f32))

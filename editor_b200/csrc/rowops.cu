@@ -38,9 +38,11 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, OutT* __restrict__ y, long long ldy,
-                                                     float* __restrict__ mean, float* __restrict__ rstd, int rows) {
+                                                     float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                                     const int* __restrict__ rows_dev) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (rows_dev != nullptr) rows = min(rows, *rows_dev);
     if (row >= rows) return;
     const float* xr = x + (size_t)row * ldx;
     float4 v[VPL];
@@ -73,16 +75,17 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 }
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
-                  long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, cudaStream_t st) {
+                  long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, const int* rows_dev,
+                  cudaStream_t st) {
     if (dim != D) return edb_set_error(EDB_ERR_SHAPE, "layernorm: only 768-wide rows are supported");
     if (rows <= 0) return EDB_OK;
     if (ldx % 4 || ldy % 4) return edb_set_error(EDB_ERR_ALIGN, "layernorm: row pitch must be a multiple of 4");
     const int grid = (rows + 7) / 8;
     if (y_f32)
-        ln_fwd_kernel<float><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, (float*)y, ldy, mean, rstd, rows);
+        ln_fwd_kernel<float><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, (float*)y, ldy, mean, rstd, rows, rows_dev);
     else
         ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y, ldy, mean, rstd,
-                                                          rows);
+                                                          rows, rows_dev);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }
@@ -98,8 +101,9 @@ ln_bwd_kernel(const DyT* __restrict__ dy, long long lddy, const float* __restric
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ g_in, float* __restrict__ g_out, long long ldg,
               __nv_bfloat16* __restrict__ g_bf16, long long ldgb, float* __restrict__ partial, int rows,
-              const float* __restrict__ row_scale, int scale_group) {
+              const float* __restrict__ row_scale, int scale_group, const int* __restrict__ rows_dev) {
     __shared__ float red[LNB_WARPS][D];
+    if (rows_dev != nullptr) rows = min(rows, *rows_dev);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 gm[VPL];
     float4 acc_g[VPL], acc_b[VPL], acc_c[VPL];
@@ -179,7 +183,8 @@ size_t layernorm_bwd_workspace_bytes() { return (size_t)num_sms() * 2 * 3 * D * 
 int layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
                   const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg,
                   void* g_bf16, long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace,
-                  size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, cudaStream_t st) {
+                  size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, const int* rows_dev,
+                  cudaStream_t st) {
     if (scale_group <= 0) scale_group = 1;
     if (dim != D) return edb_set_error(EDB_ERR_SHAPE, "layernorm_bwd: only 768-wide rows are supported");
     if (rows <= 0) return EDB_OK;
@@ -191,11 +196,11 @@ int layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, lo
     if (dy_f32)
         ln_bwd_kernel<float><<<grid, LNB_WARPS * 32, 0, st>>>((const float*)dy, lddy, x, ldx, mean, rstd, gamma, g_in,
                                                               g_out, ldg, (__nv_bfloat16*)g_bf16, ldgb, partial, rows,
-                                                              row_scale, scale_group);
+                                                              row_scale, scale_group, rows_dev);
     else
         ln_bwd_kernel<__nv_bfloat16><<<grid, LNB_WARPS * 32, 0, st>>>((const __nv_bfloat16*)dy, lddy, x, ldx, mean, rstd,
                                                                       gamma, g_in, g_out, ldg, (__nv_bfloat16*)g_bf16,
-                                                                      ldgb, partial, rows, row_scale, scale_group);
+                                                                      ldgb, partial, rows, row_scale, scale_group, rows_dev);
     EDB_CHECK_LAUNCH();
     ln_bwd_finish_kernel<<<(3 * D + 255) / 256, 256, 0, st>>>(partial, grid, dgamma, dbeta, dcol);
     EDB_CHECK_LAUNCH();
@@ -258,6 +263,40 @@ int cast_f32_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
     size_t blocks = (n4 + 255) / 256;
     if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     cast_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n4);
+    EDB_CHECK_LAUNCH();
+    return EDB_OK;
+}
+
+__global__ void cast_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int max_rows, int cols4,
+                                 const int* __restrict__ rows_dev) {
+    const size_t n4 = (size_t)min(max_rows, *rows_dev) * cols4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = load4(src + i * 4);
+        store4(dst + i * 4, v.x, v.y, v.z, v.w);
+    }
+}
+
+int cast_rows_f32_bf16(const float* src, void* dst, int max_rows, int cols, const int* rows_dev, cudaStream_t st) {
+    if (max_rows <= 0) return EDB_OK;
+    if (cols % 4) return edb_set_error(EDB_ERR_ALIGN, "cast_rows: cols must be a multiple of 4");
+    size_t blocks = ((size_t)max_rows * (cols / 4) + 255) / 256;
+    if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+    cast_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, max_rows, cols / 4, rows_dev);
+    EDB_CHECK_LAUNCH();
+    return EDB_OK;
+}
+
+__global__ void zero_rows_kernel(uint8_t* base, long long row_bytes, const int* __restrict__ rows_dev, int nrows) {
+    uint4* p = reinterpret_cast<uint4*>(base + (size_t)(*rows_dev) * row_bytes);
+    const size_t n = (size_t)nrows * row_bytes / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+int zero_rows(void* base, long long row_bytes, const int* rows_dev, int nrows, cudaStream_t st) {
+    if (nrows <= 0) return EDB_OK;
+    if (row_bytes % 16) return edb_set_error(EDB_ERR_ALIGN, "zero_rows: row size must be a multiple of 16 bytes");
+    zero_rows_kernel<<<32, 256, 0, st>>>((uint8_t*)base, row_bytes, rows_dev, nrows);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }

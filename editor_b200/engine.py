@@ -149,7 +149,8 @@ class Workspace:
             n *= int(s)
         t = self.bufs.get(name)
         if t is None or t.numel() < n or t.dtype != dtype:
-            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            # zero-filled: rows past the (device-side) row count of a packed matrix must stay finite
+            t = torch.zeros(max(n, 1), dtype=dtype, device=self.device)
             self.bufs[name] = t
         return t[:n].view(shape)
 
@@ -211,70 +212,75 @@ class EditorEngine:
             ev.append((name, e))
 
     # ------------------------------------------------------------------ building blocks
-    def _linear(self, x, L, out, rows, prec, epi=lib.EPI_STORE, aux=None, out2=None, row_scale=None, group=1):
+    def _linear(self, x, L, out, rows, prec, epi=lib.EPI_STORE, aux=None, out2=None, row_scale=None, group=1, rd=None):
+        """rows = launch bound; rd = optional device pointer to the actual row count (packed HMA rows)."""
         if prec == BF16:
             lib.gemm(x, L.w16, out, rows, L.out_f, L.in_f, epilogue=epi, bias=L.b, aux=aux, out2=out2,
-                     row_scale=row_scale, scale_group=group)
+                     row_scale=row_scale, scale_group=group, M_dev=rd)
         else:
             xs = self.ws.get("split_a", (x.shape[0], 6 * L.in_f), torch.bfloat16)
             lib.split3(x, xs, 0, rows)
             lib.gemm(xs, L.wsplit(), out, rows, L.out_f, 6 * L.in_f, epilogue=epi, bias=L.b, aux=aux, out2=out2,
-                     row_scale=row_scale, scale_group=group)
+                     row_scale=row_scale, scale_group=group, M_dev=rd)
         return out
 
-    def _wgrad(self, dy, x, L, rows):
+    def _wgrad(self, dy, x, L, rows, rd=None):
         """dW[out,in] += dy[rows,out]^T x[rows,in]   (split-K, fp32 atomic accumulate into the gradient arena)."""
         tiles = ((L.out_f + 127) // 128) * ((L.in_f + 255) // 256 if L.in_f > 128 else 1)
         split = _pick_split(tiles, (rows + 63) // 64)
-        lib.gemm(dy, x, L.gw, L.out_f, L.in_f, rows, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=split)
+        lib.gemm(dy, x, L.gw, L.out_f, L.in_f, rows, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=split, K_dev=rd)
 
-    def _block_fwd(self, x, x1, x2, rows, bp, attn, tag, prec, rs_attn=None, rs_mlp=None, group=1):
+    def _block_fwd(self, x, x1, x2, rows, bp, attn, tag, prec, rs_attn=None, rs_mlp=None, group=1, rd=None):
         """One transformer block (vit_pytorch.py:215-220 / :311-317,328-329) on `rows` packed token rows.
         x, x1, x2: fp32 residual stream before / after attention / after MLP.  Returns what the backward needs."""
         ws, cap = self.ws, x.shape[0]
         adt = torch.bfloat16 if prec == BF16 else torch.float32
         ln1 = ws.get(tag + "ln1", (cap, DIM), adt)
         m1, r1 = ws.get(tag + "m1", (cap,), torch.float32), ws.get(tag + "r1", (cap,), torch.float32)
-        lib.layernorm_fwd(x, bp.ln1.g, bp.ln1.b, bp.ln1.eps, ln1, m1, r1, rows)
+        lib.layernorm_fwd(x, bp.ln1.g, bp.ln1.b, bp.ln1.eps, ln1, m1, r1, rows, rows_dev=rd)
         qkv = ws.get(tag + "qkv", (cap, 3 * DIM), adt)
-        self._linear(ln1, bp.qkv, qkv, rows, prec)
+        self._linear(ln1, bp.qkv, qkv, rows, prec, rd=rd)
         att = ws.get(tag + "att", (cap, DIM), adt)
         P = attn(qkv, att, tag)
-        self._linear(att, bp.proj, x1, rows, prec, epi=lib.EPI_RESIDUAL, aux=x, row_scale=rs_attn, group=group)
+        self._linear(att, bp.proj, x1, rows, prec, epi=lib.EPI_RESIDUAL, aux=x, row_scale=rs_attn, group=group, rd=rd)
         ln2 = ws.get(tag + "ln2", (cap, DIM), adt)
         m2, r2 = ws.get(tag + "m2", (cap,), torch.float32), ws.get(tag + "r2", (cap,), torch.float32)
-        lib.layernorm_fwd(x1, bp.ln2.g, bp.ln2.b, bp.ln2.eps, ln2, m2, r2, rows)
+        lib.layernorm_fwd(x1, bp.ln2.g, bp.ln2.b, bp.ln2.eps, ln2, m2, r2, rows, rows_dev=rd)
         pre = ws.get(tag + "pre", (cap, HID), adt)
         h = ws.get(tag + "h", (cap, HID), adt)
-        self._linear(ln2, bp.fc1, h, rows, prec, epi=lib.EPI_GELU, out2=pre)
-        self._linear(h, bp.fc2, x2, rows, prec, epi=lib.EPI_RESIDUAL, aux=x1, row_scale=rs_mlp, group=group)
+        self._linear(ln2, bp.fc1, h, rows, prec, epi=lib.EPI_GELU, out2=pre, rd=rd)
+        self._linear(h, bp.fc2, x2, rows, prec, epi=lib.EPI_RESIDUAL, aux=x1, row_scale=rs_mlp, group=group, rd=rd)
         return dict(x=x, x1=x1, ln1=ln1, m1=m1, r1=r1, qkv=qkv, att=att, P=P, ln2=ln2, m2=m2, r2=r2, pre=pre, h=h)
 
-    def _block_bwd(self, g, gb, rows, bp, sv, attn_bwd, dcol_prev, rs_attn=None, rs_prev=None, group=1):
+    def _block_bwd(self, g, gb, rows, bp, sv, attn_bwd, dcol_prev, rs_attn=None, rs_prev=None, group=1, rd=None):
         """Backward of `_block_fwd`.  g (fp32) / gb (bf16, already DropPath-scaled): gradient w.r.t. the block output;
-        on return they hold the gradient w.r.t. the block input (gb scaled by `rs_prev`)."""
+        on return they hold the gradient w.r.t. the block input (gb scaled by `rs_prev`).  With a device-side row count
+        (rd) the 64 rows after the last valid one of every wgrad A-operand are zeroed: they pad the split-K reduction."""
         ws, cap = self.ws, g.shape[0]
-        dpre = ws.get("dpre", (cap, HID), torch.bfloat16)
-        lib.gemm(gb, bp.fc2.w16, dpre, rows, HID, DIM, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=sv["pre"])
-        self._wgrad(gb, sv["h"], bp.fc2, rows)
+        dpre = ws.get("dpre", (cap + 64, HID), torch.bfloat16)
+        dqkv = ws.get("dqkv", (cap + 64, 3 * DIM), torch.bfloat16)
+        if rd is not None:
+            for buf, width in ((gb, DIM), (dpre, HID), (dqkv, 3 * DIM)):
+                lib.call("edb_zero_rows", buf.data_ptr(), width * 2, rd, 64, lib.stream_ptr())
+        lib.gemm(gb, bp.fc2.w16, dpre, rows, HID, DIM, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=sv["pre"], M_dev=rd)
+        self._wgrad(gb, sv["h"], bp.fc2, rows, rd)
         if bp.fc1.gb is not None:
             lib.colsum(dpre, bp.fc1.gb, rows, HID)
         dln = ws.get("dln", (cap, DIM), torch.bfloat16)
-        lib.gemm(dpre, bp.fc1.w16, dln, rows, DIM, HID, b_mn=True)
-        self._wgrad(dpre, sv["ln2"], bp.fc1, rows)
+        lib.gemm(dpre, bp.fc1.w16, dln, rows, DIM, HID, b_mn=True, M_dev=rd)
+        self._wgrad(dpre, sv["ln2"], bp.fc1, rows, rd)
         lib.layernorm_bwd(dln, sv["x1"], sv["m2"], sv["r2"], bp.ln2.g, g, g, gb, bp.ln2.gg, bp.ln2.gb, bp.proj.gb, rows,
-                          row_scale=rs_attn, scale_group=group)
+                          row_scale=rs_attn, scale_group=group, rows_dev=rd)
         datt = ws.get("datt", (cap, DIM), torch.bfloat16)
-        lib.gemm(gb, bp.proj.w16, datt, rows, DIM, DIM, b_mn=True)
-        self._wgrad(gb, sv["att"], bp.proj, rows)
-        dqkv = ws.get("dqkv", (cap, 3 * DIM), torch.bfloat16)
+        lib.gemm(gb, bp.proj.w16, datt, rows, DIM, DIM, b_mn=True, M_dev=rd)
+        self._wgrad(gb, sv["att"], bp.proj, rows, rd)
         attn_bwd(sv["qkv"], sv["P"], datt, dqkv)
         if bp.qkv.gb is not None:
             lib.colsum(dqkv, bp.qkv.gb, rows, 3 * DIM)
-        lib.gemm(dqkv, bp.qkv.w16, dln, rows, DIM, 3 * DIM, b_mn=True)
-        self._wgrad(dqkv, sv["ln1"], bp.qkv, rows)
+        lib.gemm(dqkv, bp.qkv.w16, dln, rows, DIM, 3 * DIM, b_mn=True, M_dev=rd)
+        self._wgrad(dqkv, sv["ln1"], bp.qkv, rows, rd)
         lib.layernorm_bwd(dln, sv["x"], sv["m1"], sv["r1"], bp.ln1.g, g, g, gb, bp.ln1.gg, bp.ln1.gb, dcol_prev, rows,
-                          row_scale=rs_prev, scale_group=group)
+                          row_scale=rs_prev, scale_group=group, rows_dev=rd)
 
     # ------------------------------------------------------------------ backbone (3 modalities batched: S = 3B sequences)
     def backbone_forward(self, rgb, ni, ti, cam, prec, keep, droppath=None):
@@ -377,10 +383,10 @@ class EditorEngine:
         seq_off = torch.empty(B + 1, dtype=torch.int32, device=rgb.device)
         seq_off3 = torch.empty(B + 1, dtype=torch.int32, device=rgb.device)
         lib.call("edb_index_finalize", index.data_ptr(), B, seq_off.data_ptr(), seq_off3.data_ptr(), lib.stream_ptr())
-        off_host = seq_off.cpu()          # the one host sync of the forward (the reference syncs here too: make_model.py:200)
-        lens = off_host[1:] - off_host[:-1]
-        sel = dict(index=index, seq_off=seq_off, seq_off3=seq_off3, T=int(off_host[-1]), max_len=int(lens.max()), B=B,
-                   debug=dbg)
+        # static bounds from the configuration: <= HEAD_KEEP tokens per head, 12 heads, 3 modalities, + FREQUENCY_KEEP
+        ml_cap = min(NTOK, 1 + 3 * HEADS * int(m.head_keep) + int(m.FREQ_INDEX.keep))
+        sel = dict(index=index, seq_off=seq_off, seq_off3=seq_off3, B=B, ml_cap=ml_cap, T_cap=B * ml_cap,
+                   T_dev=seq_off.data_ptr() + 4 * B, T3_dev=seq_off3.data_ptr() + 4 * B, debug=dbg)
         return sel
 
     # ------------------------------------------------------------------ HMA on packed kept tokens
@@ -413,8 +419,9 @@ class EditorEngine:
         """SFTS masking (SFTS.py:208-222) + BlockMask.forward (vit_pytorch.py:309-352) + pooling
         (make_model.py:186-203) on the packed kept rows.  tokens: [3B,129,768] fp32."""
         ws = self.ws
-        B, T, ml = sel["B"], sel["T"], sel["max_len"]
-        cap = B * (1 + NPATCH)
+        B, T, ml = sel["B"], sel["T_cap"], sel["ml_cap"]          # launch bounds; actual counts stay on the device
+        td, t3d = sel["T_dev"], sel["T3_dev"]
+        cap = T
         dev = tokens.device
         xp = ws.get("hma_xp", (3, cap, DIM), torch.float32)
         loss_bcc = torch.zeros(1, dtype=torch.float32, device=dev) if training else None
@@ -425,7 +432,7 @@ class EditorEngine:
         x1all = ws.get("hma_x1", (3, cap, DIM), torch.float32)
         saved = []
         for m in range(3):
-            saved.append(self._block_fwd(xp[m], x1all[m], x2all[m], T, self.hma_blocks[m], afwd, "hma%d_" % m, prec))
+            saved.append(self._block_fwd(xp[m], x1all[m], x2all[m], T, self.hma_blocks[m], afwd, "hma%d_" % m, prec, rd=td))
         cls_mid = None
         if training:
             cls_mid = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
@@ -437,10 +444,10 @@ class EditorEngine:
         jfwd, jbwd = self._varlen_attn(sel["seq_off3"], B, 3 * ml, "hmaPj", prec, 3 * T)
         xj1 = ws.get("hma_xj1", (3 * cap, DIM), torch.float32)
         xj2 = ws.get("hma_xj2", (3 * cap, DIM), torch.float32)
-        svj = self._block_fwd(xj, xj1, xj2, 3 * T, self.hma_blocks[3], jfwd, "hmaJ_", prec)
+        svj = self._block_fwd(xj, xj1, xj2, 3 * T, self.hma_blocks[3], jfwd, "hmaJ_", prec, rd=t3d)
         xo = ws.get("hma_xo", (3 * cap, DIM), torch.float32)
         mo, ro = ws.get("hma_mo", (3 * cap,), torch.float32), ws.get("hma_ro", (3 * cap,), torch.float32)
-        lib.layernorm_fwd(xj2, self.hma_out.g, self.hma_out.b, self.hma_out.eps, xo, mo, ro, 3 * T)
+        lib.layernorm_fwd(xj2, self.hma_out.g, self.hma_out.b, self.hma_out.eps, xo, mo, ro, 3 * T, rows_dev=t3d)
         cls_out = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
         patch_mean = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
         num = torch.empty(B, dtype=torch.int32, device=dev)
@@ -451,25 +458,26 @@ class EditorEngine:
 
     def hma_backward(self, tokens, sel, sv, d_cls, d_patch, d_mid, d_bcc):
         ws = self.ws
-        B, T, ml, cap = sel["B"], sel["T"], sel["max_len"], sv["cap"]
+        B, T, ml, cap = sel["B"], sel["T_cap"], sel["ml_cap"], sv["cap"]
+        td, t3d = sel["T_dev"], sel["T3_dev"]
         dxo = ws.get("hma_dxo", (3 * cap, DIM), torch.float32)
         lib.call("edb_pool_bwd", d_cls.data_ptr(), d_patch.data_ptr(), sel["seq_off"].data_ptr(), sv["num"].data_ptr(), B,
                  ml, dxo.data_ptr(), lib.stream_ptr())
         gj = ws.get("hma_gj", (3 * cap, DIM), torch.float32)
-        gbj = ws.get("hma_gbj", (3 * cap, DIM), torch.bfloat16)
+        gbj = ws.get("hma_gbj", (3 * cap + 64, DIM), torch.bfloat16)
         lib.layernorm_bwd(dxo, sv["xj2"], sv["mo"], sv["ro"], self.hma_out.g, None, gj, gbj, self.hma_out.gg,
-                          self.hma_out.gb, None, 3 * T)
-        self._block_bwd(gj, gbj, 3 * T, self.hma_blocks[3], sv["joint"], sv["jbwd"], None)
+                          self.hma_out.gb, None, 3 * T, rows_dev=t3d)
+        self._block_bwd(gj, gbj, 3 * T, self.hma_blocks[3], sv["joint"], sv["jbwd"], None, rd=t3d)
         gm = ws.get("hma_gm", (3, cap, DIM), torch.float32)
         lib.call("edb_joint_gather", gm.data_ptr(), cap, gj.data_ptr(), sel["seq_off"].data_ptr(), B, ml, 1,
                  lib.stream_ptr())
         if d_mid is not None:
             lib.call("edb_cls_rows", gm.data_ptr(), cap, sel["seq_off"].data_ptr(), B, d_mid.data_ptr(), 1,
                      lib.stream_ptr())
-        gbm = ws.get("hma_gbm", (cap, DIM), torch.bfloat16)
+        gbm = ws.get("hma_gbm", (cap + 64, DIM), torch.bfloat16)
         for m in range(3):
-            lib.cast_bf16(gm[m], gbm, T * DIM)
-            self._block_bwd(gm[m], gbm, T, self.hma_blocks[m], sv["mods"][m], sv["abwd"], None)
+            lib.call("edb_cast_rows_f32_bf16", gm[m].data_ptr(), gbm.data_ptr(), T, DIM, td, lib.stream_ptr())
+            self._block_bwd(gm[m], gbm, T, self.hma_blocks[m], sv["mods"][m], sv["abwd"], None, rd=td)
         d_tokens = torch.empty_like(tokens)
         lib.call("edb_sfts_pack_bwd", tokens.data_ptr(), sel["index"].data_ptr(), sel["seq_off"].data_ptr(), B, cap,
                  gm.data_ptr(), lib.ptr(d_bcc), d_tokens.data_ptr(), lib.stream_ptr())

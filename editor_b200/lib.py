@@ -33,6 +33,7 @@ class GemmDesc(ctypes.Structure):
         ("alpha", c_float),
         ("split_k", c_int),
         ("row_scale", c_vp), ("scale_group", c_int),
+        ("M_dev", c_vp), ("K_dev", c_vp),
     ]
 
 
@@ -56,10 +57,13 @@ SIGNATURES = {
     "edb_version": (c_int, []),
     "edb_last_error": (ctypes.c_char_p, []),
     "edb_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), c_vp]),
-    "edb_layernorm_fwd": (c_int, [c_vp, c_ll, c_vp, c_vp, c_float, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_int, c_vp]),
+    "edb_layernorm_fwd": (c_int, [c_vp, c_ll, c_vp, c_vp, c_float, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_int, c_vp,
+                                  c_vp]),
+    "edb_cast_rows_f32_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "edb_zero_rows": (c_int, [c_vp, c_ll, c_vp, c_int, c_vp]),
     "edb_layernorm_bwd_workspace_bytes": (c_sz, []),
     "edb_layernorm_bwd": (c_int, [c_vp, c_ll, c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp,
-                                  c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp, c_int, c_vp]),
+                                  c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "edb_colsum": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_vp, c_vp]),
     "edb_cast_f32_bf16": (c_int, [c_vp, c_vp, c_sz, c_vp]),
     "edb_sgd_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_float, c_float, c_float, c_float, c_float, c_float,
@@ -129,7 +133,7 @@ def call(name, *args):
 
 
 def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None, aux=None, out2=None,
-         alpha=1.0, split_k=1, row_scale=None, scale_group=1):
+         alpha=1.0, split_k=1, row_scale=None, scale_group=1, M_dev=None, K_dev=None):
     """D[M,N] = epi(sum_k A(m,k) B(n,k)); A/B bf16 CUDA tensors, D bf16 or fp32 (2-D, row pitch = stride(0))."""
     d = GemmDesc()
     d.M, d.N, d.K = M, N, K
@@ -146,6 +150,7 @@ def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None
     d.split_k = split_k
     d.row_scale = row_scale.data_ptr() if row_scale is not None else None
     d.scale_group = scale_group
+    d.M_dev, d.K_dev = M_dev, K_dev
     if gemm_timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -157,10 +162,10 @@ def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None
     return D
 
 
-def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, rows=None):
+def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, rows=None, rows_dev=None):
     rows = x.shape[0] if rows is None else rows
     call("edb_layernorm_fwd", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
-         y.stride(0), _f32(y), ptr(mean), ptr(rstd), rows, x.shape[1], stream_ptr())
+         y.stride(0), _f32(y), ptr(mean), ptr(rstd), rows, x.shape[1], rows_dev, stream_ptr())
     return y
 
 
@@ -168,7 +173,7 @@ _ln_ws = {}
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, g_in, g_out, g_bf16, dgamma, dbeta, dcol, rows=None, row_scale=None,
-                  scale_group=1):
+                  scale_group=1, rows_dev=None):
     rows = x.shape[0] if rows is None else rows
     dev = x.device
     ws = _ln_ws.get(dev)
@@ -178,7 +183,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, g_in, g_out, g_bf16, dgamma, dbeta, 
     call("edb_layernorm_bwd", dy.data_ptr(), dy.stride(0), _f32(dy), x.data_ptr(), x.stride(0), mean.data_ptr(),
          rstd.data_ptr(), gamma.data_ptr(), ptr(g_in), ptr(g_out), ldg, ptr(g_bf16),
          g_bf16.stride(0) if g_bf16 is not None else 0, ptr(dgamma), ptr(dbeta), ptr(dcol), ws.data_ptr(), ws.numel(),
-         rows, x.shape[1], ptr(row_scale), scale_group, stream_ptr())
+         rows, x.shape[1], ptr(row_scale), scale_group, rows_dev, stream_ptr())
 
 
 def colsum(src, out, rows=None, n=None):

@@ -62,6 +62,8 @@ typedef struct EdbGemmDesc {
     int split_k;                       /* >1 only with EPI_ATOMIC */
     const float* row_scale;            /* EPI_RESIDUAL only: D = aux + row_scale[row/scale_group]*(acc+bias) -- DropPath   */
     int scale_group;                   /* (vit_pytorch.py:52-69,217-219); NULL = 1.0                                      */
+    const int* M_dev;                  /* optional DEVICE ints overriding M / K at run time (M, K then are upper bounds used  */
+    const int* K_dev;                  /* for the launch): row counts of the packed HMA matrices are produced on the GPU     */
 } EdbGemmDesc;
 
 int edb_gemm_bf16(const EdbGemmDesc* desc, void* stream);
@@ -71,7 +73,9 @@ int edb_gemm_bf16(const EdbGemmDesc* desc, void* stream);
 /* y = LayerNorm(x) over 768-wide rows; optional per-row mean / rstd for the backward.
  * Replaces nn.LayerNorm in Block (vit_pytorch.py:206,211,643, eps 1e-6) and BlockMask (:265-296, eps 1e-5). */
 int edb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
-                      long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, void* stream);
+                      long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, const int* rows_dev,
+                      void* stream);
+/* rows_dev (optional, everywhere it appears): DEVICE int with the actual row count; `rows` is then the launch bound. */
 
 /* g_out = g_in + dLN(dy) (g_in may be NULL, may alias g_out); optional bf16 copy of g_out; dgamma/dbeta/dcol are
  * ACCUMULATED (+=), dcol = column sums of g_out (the bias gradient of the Linear feeding this residual value). */
@@ -79,7 +83,8 @@ size_t edb_layernorm_bwd_workspace_bytes(void);
 int edb_layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
                       const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg,
                       void* g_bf16, long long ldgb, float* dgamma, float* dbeta, float* dcol, void* workspace,
-                      size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, void* stream);
+                      size_t ws_bytes, int rows, int dim, const float* row_scale, int scale_group, const int* rows_dev,
+                      void* stream);
 /* row_scale (optional): g_bf16 and dcol carry row_scale[row/scale_group]*g_out -- the gradient entering a DropPath-scaled
  * branch (vit_pytorch.py:52-69). */
 
@@ -88,6 +93,10 @@ int edb_colsum(const void* src, long long ld, int src_f32, int rows, int n, floa
 
 /* fp32 -> bf16 (weights once per step, activations) */
 int edb_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
+/* same over rows_dev[0] rows of `cols` contiguous elements (upper bound max_rows) */
+int edb_cast_rows_f32_bf16(const float* src, void* dst, int max_rows, int cols, const int* rows_dev, void* stream);
+/* zero `nrows` rows of `row_bytes` bytes starting at row rows_dev[0]: the K-padding of split-K wgrads over packed rows */
+int edb_zero_rows(void* base, long long row_bytes, const int* rows_dev, int nrows, void* stream);
 
 /* Fused SGD-momentum over the flat parameter arena (torch.optim.SGD semantics of
  * solver/make_optimizer.py:6-22: one group per tensor, bias lr x BIAS_LR_FACTOR, weight decay added to the gradient).
