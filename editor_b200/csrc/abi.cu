@@ -120,4 +120,37 @@ int edb_cls_rows(float* packed, long long cap, const int* seq_off, int B, float*
     return edb::cls_rows(packed, cap, seq_off, B, rows, dir, ST);
 }
 
+int edb_bn1d_fwd(const float* x, long long ldx, int B, int F, const float* gamma, const float* beta, float* run_mean,
+                 float* run_var, float momentum, float eps, float* y, long long ldy, float* save_mean,
+                 float* save_invstd, void* stream) {
+    return edb::bn1d_fwd(x, ldx, B, F, gamma, beta, run_mean, run_var, momentum, eps, y, ldy, save_mean, save_invstd, ST);
+}
+int edb_bn1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, int B, int F, const float* gamma,
+                 const float* save_mean, const float* save_invstd, float* dx, long long lddx, float* dgamma,
+                 float* dbeta, void* stream) {
+    return edb::bn1d_bwd(dy, lddy, x, ldx, B, F, gamma, save_mean, save_invstd, dx, lddx, dgamma, dbeta, ST);
+}
+int edb_ocfr_fwd(const float* x, const long long* label, int B, int C, float* c_rgb, float* c_nir, float* c_tir,
+                 float momentum, float* fn, float* inv_norm, float* loss, void* stream) {
+    return edb::ocfr_fwd(x, label, B, C, c_rgb, c_nir, c_tir, momentum, fn, inv_norm, loss, ST);
+}
+int edb_ocfr_bwd(const float* fn, const float* inv_norm, const long long* label, int B, float* c_rgb, float* c_nir,
+                 float* c_tir, const float* g_loss, float* dx, void* stream) {
+    return edb::ocfr_bwd(fn, inv_norm, label, B, c_rgb, c_nir, c_tir, g_loss, dx, ST);
+}
+int edb_ce_smooth(const float* logits, long long ld, const long long* label, int B, int C, float eps, float* loss,
+                  float* dlogits, long long ldd, void* stream) {
+    return edb::ce_smooth(logits, ld, label, B, C, eps, loss, dlogits, ldd, ST);
+}
+size_t edb_triplet_workspace_bytes(int B) { return edb::triplet_workspace_bytes(B); }
+int edb_triplet_fwd(const float* x, long long ld, const long long* label, int B, int F, float* loss, void* workspace,
+                    size_t ws_bytes, void* stream) {
+    return edb::triplet_fwd(x, ld, label, B, F, loss, workspace, ws_bytes, ST);
+}
+int edb_triplet_bwd(const float* x, long long ld, int B, int F, const void* workspace, const float* g_loss, float* dx,
+                    long long ldd, int accumulate, void* stream) {
+    return edb::triplet_bwd(x, ld, B, F, workspace, g_loss, dx, ldd, accumulate, ST);
+}
+int edb_scale_by(const float* x, const float* a, float* y, size_t n, void* stream) { return edb::scale_by(x, a, y, n, ST); }
+
 }  // extern "C"

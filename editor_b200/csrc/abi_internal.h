@@ -67,4 +67,23 @@ int pool_bwd(const float* d_cls, const float* d_patch, const int* seq_off, const
              cudaStream_t st);
 int cls_rows(float* packed, long long cap, const int* seq_off, int B, float* rows, int dir, cudaStream_t st);
 
+int bn1d_fwd(const float* x, long long ldx, int B, int F, const float* gamma, const float* beta, float* run_mean,
+             float* run_var, float momentum, float eps, float* y, long long ldy, float* save_mean, float* save_invstd,
+             cudaStream_t st);
+int bn1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, int B, int F, const float* gamma,
+             const float* save_mean, const float* save_invstd, float* dx, long long lddx, float* dgamma, float* dbeta,
+             cudaStream_t st);
+int ocfr_fwd(const float* x, const long long* label, int B, int C, float* c0, float* c1, float* c2, float mom, float* fn,
+             float* inv_norm, float* loss, cudaStream_t st);
+int ocfr_bwd(const float* fn, const float* inv_norm, const long long* label, int B, float* c0, float* c1, float* c2,
+             const float* g_loss, float* dx, cudaStream_t st);
+int ce_smooth(const float* logits, long long ld, const long long* label, int B, int C, float eps, float* loss,
+              float* dlogits, long long ldd, cudaStream_t st);
+size_t triplet_workspace_bytes(int B);
+int triplet_fwd(const float* x, long long ld, const long long* label, int B, int F, float* loss, void* workspace,
+                size_t ws_bytes, cudaStream_t st);
+int triplet_bwd(const float* x, long long ld, int B, int F, const void* workspace, const float* g, float* dx,
+                long long ldd, int accumulate, cudaStream_t st);
+int scale_by(const float* x, const float* a, float* y, size_t n, cudaStream_t st);
+
 }  // namespace edb

@@ -12,9 +12,9 @@ modeling/fusion_part/Frequency.py:42-84, modeling/fusion_part/OCFR.py:22-84.
 import ctypes
 
 import torch
-import torch.nn.functional as F
 
 from . import lib
+from . import tail as _tail
 
 DIM, HEADS, HID, NTOK, NPATCH = 768, 12, 3072, 129, 128
 P_LD = 136                      # pitch of the stored attention maps (129 padded to a 16-byte multiple)
@@ -199,6 +199,9 @@ class EditorEngine:
                            for n1, at, n2, ml in (("normR", "attnR", "normR_", "mlpR"), ("normN", "attnN", "normN_", "mlpN"),
                                                   ("normT", "attnT", "normT_", "mlpT"), ("norm1", "attn1", "norm2", "mlp"))]
         self.hma_out = _Norm(self, f + "out_norm", 1e-5)
+        self.tail_lin = {n: _Lin(self, n + ".weight", (n + ".bias") if (n + ".bias") in self.arena.offsets else None)
+                         for n in ("RGB_REDUCE", "NIR_REDUCE", "TIR_REDUCE", "FUSE_HEAD", "BACKBONE_HEAD", "AL_HEAD")
+                         if (n + ".weight") in self.arena.offsets}
         self.bb_names = [n for n in self.arena.names if n.startswith("BACKBONE.base.") and ".fc." not in n]
         self.hma_names = [n for n in self.arena.names if n.startswith("FUSE_block.")]
         self.bb_plist = [self.arena.params[self.arena.names.index(n)] for n in self.bb_names]
@@ -528,53 +531,34 @@ class EditorEngine:
                 self.sel = sel
                 cls_out, patch_mean, _, _, num, _ = self.hma_forward(tokens, sel, prec, False)
                 self.last = dict(tokens=tokens, num=num)
-                with torch.autocast("cuda", enabled=False):
-                    return self._reduce(cls_out, patch_mean)
+                return self._reduce(cls_out, patch_mean, prec)
         self.arena.grad.zero_()
         dp = self._droppath(B, rgb.device)
         tokens = _BackboneFn.apply(self, rgb, ni, ti, cam, prec, dp, *self.bb_plist)
         tok = tokens.view(3, B, NTOK, DIM)
         cls_bb = [tok[i, :, 0] for i in range(3)]
+        lin, BN, LIN = self.tail_lin, _tail.BatchNormFn.apply, _tail.LinearFn.apply
         if m.AL:
             ori = torch.cat(cls_bb, dim=-1)
-            ori_score = m.AL_HEAD(m.AL_BN(ori))
-        else:
-            scores = [m.BACKBONE_HEAD(m.BACKBONE_BN(c)) for c in cls_bb]
+            ori_score = LIN(self, lin["AL_HEAD"], prec, BN(self, "AL_BN", m.AL_BN, ori))
+        else:   # three separate BN calls, each with its own batch statistics (SURVEY.md App. A-11)
+            scores = [LIN(self, lin["BACKBONE_HEAD"], prec, BN(self, "BACKBONE_BN", m.BACKBONE_BN, c)) for c in cls_bb]
         cls_out, patch_mean, cls_mid, loss_bcc = _HMAFn.apply(self, tokens, prec, *self.hma_plist)
-        loss_ocfr = self._ocfr(cls_mid, label)
+        loss_ocfr = _tail.OcfrFn.apply(m.FUSE_block.memory_cls, cls_mid, label)
         if writer is not None:
             writer.add_scalar("num_count", self.last["num"].float().mean(), epoch)      # make_model.py:199-200
-        cls4t = self._reduce(cls_out, patch_mean)
-        score = m.FUSE_HEAD(m.FUSE_BN(cls4t))
-        aux = loss_bcc.reshape(()) + loss_ocfr
+        cls4t = self._reduce(cls_out, patch_mean, prec)
+        score = LIN(self, lin["FUSE_HEAD"], prec, BN(self, "FUSE_BN", m.FUSE_BN, cls4t))
+        aux = loss_bcc.reshape(()) + loss_ocfr.reshape(())
         if m.AL:
             return score, cls4t, ori_score, ori, aux
         return score, cls4t, scores[0], cls_bb[0], scores[1], cls_bb[1], scores[2], cls_bb[2], aux
 
-    def _reduce(self, cls_out, patch_mean):
-        m = self.model
-        outs = [lin(torch.cat([cls_out[i], patch_mean[i]], dim=-1))
-                for i, lin in enumerate((m.RGB_REDUCE, m.NIR_REDUCE, m.TIR_REDUCE))]          # make_model.py:205-208
+    def _reduce(self, cls_out, patch_mean, prec):
+        """*_REDUCE(cat(cls, patch mean)) and the concatenation to cls4t [B, 2304] (make_model.py:205-208)."""
+        outs = [_tail.LinearFn.apply(self, self.tail_lin[n], prec, torch.cat([cls_out[i], patch_mean[i]], dim=-1))
+                for i, n in enumerate(("RGB_REDUCE", "NIR_REDUCE", "TIR_REDUCE"))]
         return torch.cat(outs, dim=-1)
-
-    def _ocfr(self, cls_mid, label):
-        """OCFR.forward (OCFR.py:44-84) without host syncs: per-ID batch centres of the L2-normalised cls tokens, EMA
-        into the memory bank (before the loss, :53), MSE(centres[label], feat).  Equals the reference for the P x K
-        contiguous labels it assumes (:33-36)."""
-        mem = self.model.FUSE_block.memory_cls
-        C = mem.RGB_centers.shape[0]
-        loss = 0
-        with torch.autocast("cuda", enabled=False):
-            ones = torch.ones(label.shape[0], dtype=torch.float32, device=label.device)
-            cnt = torch.zeros(C, dtype=torch.float32, device=label.device).index_add_(0, label, ones)
-            present = (cnt > 0).unsqueeze(1)
-            for i, cen in enumerate((mem.RGB_centers, mem.NIR_centers, mem.TIR_centers)):
-                f = F.normalize(cls_mid[i].float(), dim=1)
-                sums = torch.zeros_like(cen.data).index_add_(0, label, f.detach())
-                bc = sums / cnt.clamp(min=1).unsqueeze(1)
-                cen.data.copy_(torch.where(present, mem.momentum * bc + (1 - mem.momentum) * cen.data, cen.data))
-                loss = loss + F.mse_loss(cen.data[label], f)
-        return loss
 
 
 class _BackboneFn(torch.autograd.Function):

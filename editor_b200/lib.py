@@ -85,6 +85,16 @@ SIGNATURES = {
     "edb_pool_fwd": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "edb_pool_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     "edb_cls_rows": (c_int, [c_vp, c_ll, c_vp, c_int, c_vp, c_int, c_vp]),
+    "edb_bn1d_fwd": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_float, c_float, c_vp, c_ll, c_vp, c_vp,
+                             c_vp]),
+    "edb_bn1d_bwd": (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp]),
+    "edb_ocfr_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp]),
+    "edb_ocfr_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "edb_ce_smooth": (c_int, [c_vp, c_ll, c_vp, c_int, c_int, c_float, c_vp, c_vp, c_ll, c_vp]),
+    "edb_triplet_workspace_bytes": (c_sz, [c_int]),
+    "edb_triplet_fwd": (c_int, [c_vp, c_ll, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "edb_triplet_bwd": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_int, c_vp]),
+    "edb_scale_by": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None

@@ -3,38 +3,11 @@ gradient allreduce over the flat arena (the one collective of the path, processo
 update (solver/make_optimizer.py:6-22).  Rows f-1 / f-2 of SURVEY.md section 8: the loss is still plain torch ops."""
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from . import lib
 
 
-def label_smooth_ce(logits, target, eps=0.1):
-    """CrossEntropyLabelSmooth (layers/softmax_loss.py:23-34) without the reference's .cpu() round trip."""
-    logp = F.log_softmax(logits.float(), dim=1)
-    C = logits.shape[1]
-    nll = -logp.gather(1, target.unsqueeze(1)).squeeze(1)
-    smooth = -logp.sum(1) / C
-    return ((1 - eps) * nll + eps * smooth).sum() / logits.shape[0]
-
-
-def triplet_soft_margin(feat, label):
-    """TripletLoss(margin=None): batch-hard mining + SoftMarginLoss (layers/triplet_loss.py:16-31,51-105,122-136)."""
-    feat = feat.float()
-    xx = feat.pow(2).sum(1, keepdim=True)
-    dist_m = (xx + xx.t() - 2 * feat @ feat.t()).clamp(min=1e-12).sqrt()
-    same = label.unsqueeze(0) == label.unsqueeze(1)
-    ap = torch.where(same, dist_m, dist_m.new_full((), -1e30)).max(1).values
-    an = torch.where(~same, dist_m, dist_m.new_full((), 1e30)).min(1).values
-    return F.soft_margin_loss(an - ap, torch.ones_like(an))
-
-
-def editor_loss(outputs, label, id_w=1.0, tri_w=1.0):
-    """engine/processor.py:82-92: sum over (score, feat) pairs + trailing aux loss."""
-    with torch.autocast("cuda", enabled=False):
-        total = outputs[-1].float()
-        for i in range(0, len(outputs) - 1, 2):
-            total = total + id_w * label_smooth_ce(outputs[i], label) + tri_w * triplet_soft_margin(outputs[i + 1], label)
-    return total
+from .tail import editor_loss  # noqa: E402,F401  (CUDA kernels: label-smoothed CE + batch-hard soft-margin triplet)
 
 
 class Trainer:

@@ -186,6 +186,41 @@ int edb_pool_bwd(const float* d_cls, const float* d_patch, const int* seq_off, c
  * (vit_pytorch.py:319-323). */
 int edb_cls_rows(float* packed, long long cap, const int* seq_off, int B, float* rows, int dir, void* stream);
 
+/* ---- tail of EDITOR.forward and the loss (tiny [B, 768..2304] tensors) -------------------------------------- */
+
+/* nn.BatchNorm1d, training mode (BNNeck: FUSE_BN / AL_BN / BACKBONE_BN, make_model.py:114-141,165-171,209): batch
+ * statistics, running_mean/var updated in place (momentum 0.1, unbiased variance), mean / invstd saved for bwd. */
+int edb_bn1d_fwd(const float* x, long long ldx, int B, int F, const float* gamma, const float* beta, float* run_mean,
+                 float* run_var, float momentum, float eps, float* y, long long ldy, float* save_mean,
+                 float* save_invstd, void* stream);
+/* dgamma / dbeta are accumulated (+=) */
+int edb_bn1d_bwd(const float* dy, long long lddy, const float* x, long long ldx, int B, int F, const float* gamma,
+                 const float* save_mean, const float* save_invstd, float* dx, long long lddx, float* dgamma,
+                 float* dbeta, void* stream);
+
+/* OCFR.forward (fusion_part/OCFR.py:44-84) on x = cls tokens [3][B][768]: L2-normalise, per-id batch centres, EMA into the
+ * three [C][768] memory banks (before the loss), loss (pre-zeroed) += sum_m MSE(centres[label], fn).  fn / inv_norm are
+ * kept for the backward. */
+int edb_ocfr_fwd(const float* x, const long long* label, int B, int C, float* c_rgb, float* c_nir, float* c_tir,
+                 float momentum, float* fn, float* inv_norm, float* loss, void* stream);
+int edb_ocfr_bwd(const float* fn, const float* inv_norm, const long long* label, int B, float* c_rgb, float* c_nir,
+                 float* c_tir, const float* g_loss, float* dx, void* stream);
+
+/* CrossEntropyLabelSmooth (layers/softmax_loss.py:23-34): loss (pre-zeroed) += value; dlogits (optional) = d loss/d logits */
+int edb_ce_smooth(const float* logits, long long ld, const long long* label, int B, int C, float eps, float* loss,
+                  float* dlogits, long long ldd, void* stream);
+
+/* TripletLoss(margin=None) (layers/triplet_loss.py:16-31,51-105,122-136): fp32 pairwise distances, batch-hard mining,
+ * SoftMarginLoss.  fwd fills the workspace (distances, indices, coefficients) that bwd consumes. */
+size_t edb_triplet_workspace_bytes(int B);
+int edb_triplet_fwd(const float* x, long long ld, const long long* label, int B, int F, float* loss, void* workspace,
+                    size_t ws_bytes, void* stream);
+int edb_triplet_bwd(const float* x, long long ld, int B, int F, const void* workspace, const float* g_loss, float* dx,
+                    long long ldd, int accumulate, void* stream);
+
+/* y[i] = a[0] * x[i] (a on the device): upstream-gradient scaling of a pre-computed gradient */
+int edb_scale_by(const float* x, const float* a, float* y, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

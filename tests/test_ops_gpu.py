@@ -326,3 +326,88 @@ def test_rollout_topk_bf16_maps():
     safe = ((kth[..., 1] - kth[..., 2]) / kth[..., 1] > 1e-3).all(1)     # rows whose top-2 is not a near-tie
     want = orc.part_attention_mask(mf, 2)
     assert safe.sum() >= S - 1 and torch.equal(got[safe], want[safe])
+
+
+def test_tail_batchnorm_linear_ocfr_match_torch():
+    from editor_b200 import lib, tail
+    import __graft_entry__ as ge
+    model, sd, x, label, cam, al = ge._small_case(True, 4)
+    model = model.cuda().train()
+    eng = model.engine()
+    eng._ensure(torch.device("cuda", 0))
+    eng.arena.refresh16()
+    B = 16
+    g = _g(4)
+    # --- BatchNorm1d
+    xin = torch.randn(B, 2304, generator=g).cuda().requires_grad_(True)
+    bn_ref = torch.nn.BatchNorm1d(2304).cuda().train()
+    bn_ref.load_state_dict(model.FUSE_BN.state_dict())
+    y = tail.BatchNormFn.apply(eng, "FUSE_BN", model.FUSE_BN, xin)
+    xr = xin.detach().clone().requires_grad_(True)
+    yr = bn_ref(xr)
+    assert _rel(y, yr.detach()) < 1e-5
+    assert _rel(model.FUSE_BN.running_var, bn_ref.running_var) < 1e-6 and _rel(model.FUSE_BN.running_mean, bn_ref.running_mean) < 1e-5
+    dy = torch.randn(B, 2304, generator=g).cuda()
+    eng.arena.grad.zero_()
+    y.backward(dy)
+    yr.backward(dy)
+    assert _rel(xin.grad, xr.grad) < 1e-4
+    assert _rel(model.FUSE_BN.weight.grad, bn_ref.weight.grad) < 1e-4 and _rel(model.FUSE_BN.bias.grad, bn_ref.bias.grad) < 1e-4
+    # --- Linear (REDUCE with bias, head without, N = 171)
+    for name, K in (("RGB_REDUCE", 1536), ("FUSE_HEAD", 2304)):
+        L = eng.tail_lin[name]
+        mod = getattr(model, name)
+        xi = (torch.randn(B, K, generator=g) * 0.5).cuda().requires_grad_(True)
+        eng.arena.grad.zero_()
+        mod.weight.grad = None
+        yo = tail.LinearFn.apply(eng, L, "bf16", xi)
+        ref = torch.nn.functional.linear(xi.detach().to(torch.bfloat16).float(), mod.weight.detach().to(torch.bfloat16).float(),
+                                         None if mod.bias is None else mod.bias.detach())
+        assert _rel(yo, ref) < 2e-3
+        do = torch.randn_like(ref)
+        yo.backward(do)
+        dob = do.to(torch.bfloat16).float()
+        assert _rel(xi.grad, dob @ mod.weight.detach().to(torch.bfloat16).float()) < 2e-3
+        assert _rel(mod.weight.grad, dob.t() @ xi.detach().to(torch.bfloat16).float()) < 2e-3
+        if mod.bias is not None:
+            assert _rel(mod.bias.grad, do.sum(0)) < 1e-4
+    # --- OCFR
+    mem = model.FUSE_block.memory_cls
+    C = mem.RGB_centers.shape[0]
+    cen0 = [torch.randn(C, 768, generator=g) * 0.05 for _ in range(3)]
+    for p, c in zip((mem.RGB_centers, mem.NIR_centers, mem.TIR_centers), cen0):
+        p.data.copy_(c.cuda())
+    lab = torch.tensor([3, 3, 3, 3, 9, 9, 9, 9, 0, 0, 0, 0, 170, 170, 170, 170])
+    cm = torch.randn(3, B, 768, generator=g).cuda().requires_grad_(True)
+    loss = tail.OcfrFn.apply(mem, cm, lab.cuda())
+    cr = cm.detach().cpu().clone().requires_grad_(True)
+    cen_ref = [c.clone() for c in cen0]
+    lr = orc.ocfr([cr[0], cr[1], cr[2]], lab, cen_ref)
+    assert abs(loss.item() - lr.item()) < 1e-5 * max(1.0, abs(lr.item()))
+    for p, c in zip((mem.RGB_centers, mem.NIR_centers, mem.TIR_centers), cen_ref):
+        assert _rel(p.data.cpu(), c) < 1e-5
+    (loss * 3.0).backward()
+    (lr * 3.0).backward()
+    assert _rel(cm.grad.cpu(), cr.grad) < 1e-4
+
+
+def test_loss_kernels_match_oracle_loss():
+    from editor_b200 import tail
+    B, C, F = 32, 171, 2304
+    g = _g(6)
+    label = torch.arange(8).repeat_interleave(4)
+    logits = (torch.randn(B, C, generator=g) * 3).cuda().requires_grad_(True)
+    feat = torch.randn(B, F, generator=g).cuda().requires_grad_(True)
+    feat2 = (torch.randn(B, 768, generator=g) * 0.1).cuda().requires_grad_(True)
+    aux = torch.tensor(0.7, device="cuda", requires_grad=True)
+    outs = (logits, feat, logits * 0.5, feat2, aux)
+    loss = tail.editor_loss(outs, label.cuda())
+    ref_in = [t.detach().cpu().clone().requires_grad_(True) for t in (logits, feat, feat2, aux)]
+    lr = orc.reference_loss((ref_in[0], ref_in[1], ref_in[0] * 0.5, ref_in[2], ref_in[3]), label)
+    assert abs(loss.item() - lr.item()) < 1e-5 * abs(lr.item())
+    (loss * 2.0).backward()
+    (lr * 2.0).backward()
+    assert _rel(logits.grad.cpu(), ref_in[0].grad) < 1e-4
+    assert _rel(feat.grad.cpu(), ref_in[1].grad) < 1e-4
+    assert _rel(feat2.grad.cpu(), ref_in[2].grad) < 1e-4
+    assert abs(aux.grad.item() - 2.0) < 1e-6
