@@ -267,6 +267,23 @@ def main():
     eng.stats["events"] = None
     breakdown = {"%s->%s" % (a[0], b[0]): round(a[1].elapsed_time(b[1]), 3) for a, b in zip(ev[:-1], ev[1:])}
     barrier()
+    # ---- secondary number: eval forward (fp32-faithful mode is what engine/processor.py:176-186 runs; bf16 also shown)
+    eval_rates = {}
+    model.eval()
+    for mode in ("bf16", "fp32"):
+        model.precision = mode
+        nrep = 3 if mode == "bf16" else 1
+        model(xg, cam_label=cg)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(nrep):
+            model(xg, cam_label=cg)
+        a1.record()
+        barrier()
+        eval_rates[mode] = world * B * nrep / (a0.elapsed_time(a1) * 1e-3)
+    model.precision = "auto"
+    model.train()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -290,7 +307,7 @@ def main():
             "step_tflops_of_peak": {"algorithmic_gflop_per_image": step_gflop_img,
                                     "achieved_tflops_per_gpu": step_gflop_img * B / ms_step,
                                     "frac_of_peak": step_gflop_img * B / ms_step / peak_s},
-            "roofline": roof, "phase_ms": breakdown, "loss": float(loss_host)}
+            "roofline": roof, "phase_ms": breakdown, "eval_forward_images_per_sec": eval_rates, "loss": float(loss_host)}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, t_step = cpu_oracle_rate(4, 2, 1, sd)

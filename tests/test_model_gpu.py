@@ -107,3 +107,44 @@ def test_state_dict_schema_and_config_surface():
     own = model.state_dict()
     assert list(own.keys()) == list(sd.keys())
     assert all(own[k].shape == sd[k].shape for k in sd)
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json full size (B = 128 per GPU): size-independent properties of the CUDA path.
+    (a) a sample's result does not depend on the batch it is computed in: B=128 in one call == 4 calls of 32 -- bit-exact for
+        the selection index and the pooled count, and to fp32 round-off for the features;
+    (b) permuting the samples permutes the outputs."""
+    model, sd, x, label, cam, _ = ge._small_case(True, 128)
+    model = model.cuda().eval()
+    model.precision = "bf16"            # the benchmarked mode
+    xg = {k: v.cuda() for k, v in x.items()}
+    camg = cam.cuda()
+    full = model(xg, cam_label=camg).clone()
+    idx_full = model.engine().sel["index"].clone()
+    num_full = model.engine().last["num"].clone()
+    assert torch.isfinite(full).all() and full.shape == (128, 2304)
+    parts, idxs = [], []
+    for c in range(4):
+        sl = slice(32 * c, 32 * c + 32)
+        parts.append(model({k: v[sl].contiguous() for k, v in xg.items()}, cam_label=camg[sl]).clone())
+        idxs.append(model.engine().sel["index"].clone())
+    assert torch.equal(torch.cat(idxs), idx_full)
+    assert _rel(torch.cat(parts), full) < 1e-5
+    perm = torch.randperm(128, generator=torch.Generator().manual_seed(0)).cuda()
+    out_p = model({k: v[perm].contiguous() for k, v in xg.items()}, cam_label=camg[perm])
+    assert torch.equal(model.engine().sel["index"], idx_full[perm])
+    assert torch.equal(model.engine().last["num"], num_full[perm])
+    assert _rel(out_p, full[perm]) < 1e-5
+    n = num_full.float()
+    assert n.min() >= 10 and n.max() <= 82        # FREQUENCY_KEEP <= kept <= 3*12*HEAD_KEEP + FREQUENCY_KEEP
+
+
+def test_training_steps_reduce_the_loss():
+    """Three Trainer steps (CUDA forward/backward/SGD) on a fixed batch lower the loss -- gradients have the right sign."""
+    from editor_b200.train import Trainer
+    model, sd, x, label, cam, _ = ge._small_case(True, 16)
+    model = model.cuda().train()
+    tr = Trainer(model, lr=0.01)
+    xg = {k: v.cuda() for k, v in x.items()}
+    losses = [tr.step(xg, label.cuda(), cam.cuda())[0].item() for _ in range(4)]
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0], losses
