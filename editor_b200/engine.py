@@ -521,8 +521,8 @@ class EditorEngine:
         cam = cam_label.to(torch.int64).contiguous()
         training = m.training
         prec = self._precision(training)
-        if training and prec != BF16:
-            raise lib.EdbError("training runs in the bf16 tensor-core mode only (fp32 backward is not implemented)")
+        # training forward also runs fp32-faithful (model.precision = "fp32"): outputs / loss / selection to 1e-3 of the
+        # reference; its backward is not implemented (the autograd Functions raise)
         self.arena.refresh16()
         if not training:
             with torch.no_grad():
@@ -569,12 +569,14 @@ class _BackboneFn(torch.autograd.Function):
         eng._mark("bb_fwd_end")
         eng.sel = eng.select(rgb, ni, ti, sv["maps"], prec, want_debug=eng.stats.get("debug", False))
         eng._mark("select_end")
-        ctx.eng, ctx.sv, ctx.nparams = eng, sv, len(params)
+        ctx.eng, ctx.sv, ctx.nparams, ctx.prec = eng, sv, len(params), prec
         return tokens
 
     @staticmethod
     def backward(ctx, d_tokens):
         eng = ctx.eng
+        if ctx.prec != BF16:
+            raise lib.EdbError("backward is implemented for the bf16 tensor-core mode only")
         eng._mark("bb_bwd_start")
         eng.backbone_backward(ctx.sv, d_tokens.contiguous().float())
         eng._mark("bb_bwd_end")
@@ -589,13 +591,15 @@ class _HMAFn(torch.autograd.Function):
         cls_out, patch_mean, cls_mid, loss_bcc, num, sv = eng.hma_forward(tokens, eng.sel, prec, True)
         eng._mark("hma_fwd_end")
         eng.last = dict(num=num, tokens=tokens)
-        ctx.eng, ctx.sv, ctx.sel, ctx.nparams = eng, sv, eng.sel, len(params)
+        ctx.eng, ctx.sv, ctx.sel, ctx.nparams, ctx.prec = eng, sv, eng.sel, len(params), prec
         ctx.save_for_backward(tokens)
         return cls_out, patch_mean, cls_mid, loss_bcc
 
     @staticmethod
     def backward(ctx, d_cls, d_patch, d_mid, d_bcc):
         eng = ctx.eng
+        if ctx.prec != BF16:
+            raise lib.EdbError("backward is implemented for the bf16 tensor-core mode only")
         (tokens,) = ctx.saved_tensors
         z = lambda t, ref: torch.zeros_like(ref) if t is None else t.contiguous().float()   # noqa: E731
         shape_ref = torch.empty(3, ctx.sel["B"], DIM, device=tokens.device)

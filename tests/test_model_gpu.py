@@ -148,3 +148,51 @@ def test_training_steps_reduce_the_loss():
     xg = {k: v.cuda() for k, v in x.items()}
     losses = [tr.step(xg, label.cuda(), cam.cuda())[0].item() for _ in range(4)]
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_single_and_ragged_batch_eval(B):
+    """BASELINE.json configs[0]: a single 3-modal sample through make_model(cfg=RGBNT201); also an odd batch size."""
+    model, sd, x, label, cam, _ = ge._small_case(True, B)
+    model = model.cuda().eval()
+    out = model({k: v.cuda() for k, v in x.items()}, cam_label=cam.cuda())
+    aux = {}
+    with torch.no_grad():
+        ref = orc.editor_forward(sd, x, cam, training=False, al=True, aux=aux)
+    assert out.shape == (B, 2304)
+    assert torch.equal(_bits(model.engine().sel["index"]), aux["index"])
+    assert _rel(out.cpu(), ref) < 1e-3
+
+
+def test_wrong_image_size_raises_like_the_reference():
+    model, sd, x, label, cam, _ = ge._small_case(True, 2)
+    model = model.cuda().eval()
+    bad = {k: v[:, :, :128].contiguous().cuda() for k, v in x.items()}
+    with pytest.raises(AssertionError):
+        model(bad, cam_label=cam.cuda())            # vit_pytorch.py:453-454
+
+
+@pytest.mark.parametrize("al", [True, False])
+def test_train_forward_fp32_matches_reference_golden(al):
+    """Training-mode forward in the fp32-faithful mode against the UNMODIFIED reference's outputs (tests/golden): the
+    5-/9-tuple, the loss, the selection, BN running statistics and OCFR centres after the step."""
+    model, sd, x, label, cam, _ = ge._small_case(al, 4)
+    model = model.cuda().train()
+    model.precision = "fp32"
+    outs = model({k: v.cuda() for k, v in x.items()}, label=label.cuda(), cam_label=cam.cuda(), writer=None, epoch=1)
+    g = torch.load(os.path.join(HERE, "golden", "ref_%s.pt" % ("rgbnt201" if al else "rgbnt100")), weights_only=False)
+    assert torch.equal(_bits(model.engine().sel["index"]), g["train_index"])        # index: bit-exact
+    assert len(outs) == len(g["train_outputs"])
+    for a, b in zip(outs, g["train_outputs"]):
+        assert a.shape == b.shape
+        assert _rel(a.float().cpu(), b) < 1e-3                                         # tolerance: 1e-3 rel (fp32)
+    loss = orc.reference_loss([o.float().cpu() for o in outs], label)
+    assert abs(loss.item() - g["loss"].item()) < 1e-3 * abs(g["loss"].item())
+    st = model.state_dict()
+    for k, ref in g["state_after"].items():
+        got = st[k].cpu()
+        if "centers" in k:
+            got = got[label.unique()]
+        assert _rel(got.float(), ref.float()) < 1e-3, k
+    with pytest.raises(Exception):
+        outs[0].sum().backward()                   # fp32 backward is not built: must fail loudly, not silently
