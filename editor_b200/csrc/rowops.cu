@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(LNB_WARPS * 32)
 ln_bwd_kernel(const DyT* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const float* __restrict__ g_in, float* __restrict__ g_out, long long ldg,
-              __nv_bfloat16* __restrict__ g_bf16, long long ldgb, float* __restrict__ partial, int rows,
-              const float* __restrict__ row_scale, int scale_group, const int* __restrict__ rows_dev) {
+              __nv_bfloat16* __restrict__ g_bf16, long long ldgb, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dcol, int rows, const float* __restrict__ row_scale, int scale_group,
+              const int* __restrict__ rows_dev) {
     __shared__ float red[LNB_WARPS][D];
     if (rows_dev != nullptr) rows = min(rows, *rows_dev);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -157,28 +158,18 @@ ln_bwd_kernel(const DyT* __restrict__ dy, long long lddy, const float* __restric
             store4(&red[warp][(j * 32 + lane) * 4], a.x, a.y, a.z, a.w);
         }
         __syncthreads();
+        float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dcol);
+        if (dst == nullptr) continue;      // uniform across the block
         for (int c = threadIdx.x; c < D; c += LNB_WARPS * 32) {
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < LNB_WARPS; ++w) s += red[w][c];
-            partial[(size_t)blockIdx.x * (3 * D) + which * D + c] = s;
+            atomicAdd(dst + c, s);         // ~300 CTAs x 768 columns: cheaper than a second launch per LayerNorm
         }
     }
 }
 
-// out[k][c] (+)= sum_cta partial[cta][k*768 + c] for the requested outputs
-__global__ void ln_bwd_finish_kernel(const float* __restrict__ partial, int nparts, float* dgamma, float* dbeta,
-                                     float* dcol) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 3 * D) return;
-    float* dst = c < D ? dgamma : (c < 2 * D ? dbeta : dcol);
-    if (dst == nullptr) return;
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * (3 * D) + c];
-    dst[c % D] += s;
-}
-
-size_t layernorm_bwd_workspace_bytes() { return (size_t)num_sms() * 2 * 3 * D * sizeof(float); }
+size_t layernorm_bwd_workspace_bytes() { return 256; }   // kept in the ABI; the reduction now uses atomics
 
 int layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, long long ldx, const float* mean,
                   const float* rstd, const float* gamma, const float* g_in, float* g_out, long long ldg,
@@ -192,17 +183,16 @@ int layernorm_bwd(const void* dy, long long lddy, int dy_f32, const float* x, lo
     int grid = num_sms() * 2;
     const int need = (rows + LNB_WARPS - 1) / LNB_WARPS;
     if (grid > need) grid = need;
-    float* partial = static_cast<float*>(workspace);
+    (void)workspace;
     if (dy_f32)
         ln_bwd_kernel<float><<<grid, LNB_WARPS * 32, 0, st>>>((const float*)dy, lddy, x, ldx, mean, rstd, gamma, g_in,
-                                                              g_out, ldg, (__nv_bfloat16*)g_bf16, ldgb, partial, rows,
-                                                              row_scale, scale_group, rows_dev);
+                                                              g_out, ldg, (__nv_bfloat16*)g_bf16, ldgb, dgamma, dbeta,
+                                                              dcol, rows, row_scale, scale_group, rows_dev);
     else
         ln_bwd_kernel<__nv_bfloat16><<<grid, LNB_WARPS * 32, 0, st>>>((const __nv_bfloat16*)dy, lddy, x, ldx, mean, rstd,
                                                                       gamma, g_in, g_out, ldg, (__nv_bfloat16*)g_bf16,
-                                                                      ldgb, partial, rows, row_scale, scale_group, rows_dev);
-    EDB_CHECK_LAUNCH();
-    ln_bwd_finish_kernel<<<(3 * D + 255) / 256, 256, 0, st>>>(partial, grid, dgamma, dbeta, dcol);
+                                                                      ldgb, dgamma, dbeta, dcol, rows, row_scale, scale_group,
+                                                                      rows_dev);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }

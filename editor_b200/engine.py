@@ -331,8 +331,15 @@ class EditorEngine:
         return tokens, dict(blocks=saved, x_last=x, mf=mf, rf=rf, maps=maps, patches=patches, B=B, cam=cam,
                             droppath=droppath)
 
+    def _grad_stage(self, stage):
+        """Tell the trainer that a contiguous slice of the gradient arena is final (bucketed allreduce, train.py)."""
+        hook = self.stats.get("grad_hook")
+        if hook is not None:
+            hook(stage)
+
     def backbone_backward(self, sv, d_tokens):
         ws, a = self.ws, self.arena
+        self._grad_stage("after_backbone")      # BackboneFn runs last: every tail / HMA gradient is complete
         B = sv["B"]
         S, R = 3 * B, 3 * B * NTOK
         dp = sv["droppath"]
@@ -352,6 +359,8 @@ class EditorEngine:
             rs_a = None if dp is None else dp[2 * l]
             rs_prev = None if (dp is None or l == 0) else dp[2 * l - 1]
             self._block_bwd(g, gb, R, bp, sv["blocks"][l], attn_bwd, prev_gb, rs_a, rs_prev, NTOK)
+            if l in (8, 4):
+                self._grad_stage("blocks_from_%d" % l)
         base = "BACKBONE.base."
         dpatch = ws.get("dpatch", (S * NPATCH, DIM), torch.bfloat16)
         dpos = a.gview(base + "pos_embed").view(NTOK, DIM)
@@ -361,6 +370,7 @@ class EditorEngine:
         a.gview(base + "cls_token").view(DIM).add_(dpos[0])
         lib.colsum(dpos[1:], self.patch.gb, NPATCH, DIM)
         self._wgrad(dpatch, sv["patches"], self.patch, S * NPATCH)
+        self._grad_stage("rest")
 
     # ------------------------------------------------------------------ SFTS selection (no gradient)
     def select(self, rgb, ni, ti, maps, prec, want_debug=False):

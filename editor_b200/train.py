@@ -35,22 +35,36 @@ class Trainer:
         self.first = True
         self.tail = [(n, p) for n, p in zip(arena.names, arena.params)
                      if not (n.startswith("BACKBONE.base.") or n.startswith("FUSE_block."))]
+        # gradient buckets = contiguous arena slices in the order the backward completes them (the arena follows
+        # named_parameters(): backbone embeddings, blocks 0..11, norm, fc, then FUSE_block and the heads)
+        off = lambda n: arena.offsets[n][0]                                    # noqa: E731
+        b8, b4 = off("BACKBONE.base.blocks.8.norm1.weight"), off("BACKBONE.base.blocks.4.norm1.weight")
+        after = off("FUSE_block.normR.weight")
+        self.buckets = {"after_backbone": (after, arena.total), "blocks_from_8": (b8, after), "blocks_from_4": (b4, b8),
+                        "rest": (0, b4)}
+        self.pending = []
+
+    def _on_grad_stage(self, stage):
+        """Called by the engine during backward: allreduce the finished slice on NCCL's stream while the remaining
+        dgrad/wgrad GEMMs keep running (the one collective of the path, overlapped)."""
+        if self.world == 1:
+            return
+        a, b = self.buckets[stage]
+        arena = self.model.engine().arena
+        self.pending.append(dist.all_reduce(arena.grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
 
     def step(self, x, label, cam, writer=None, epoch=1):
         model = self.model
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outputs = model(x, label=label, cam_label=cam, view_label=None, img_path=None, writer=writer, epoch=epoch)
             loss = editor_loss(outputs, label)
-        for _, p in getattr(self, "tail", []):
-            p.grad = None
-        loss.backward()
         arena = model.engine().arena
         self._setup(arena)
-        for n, p in self.tail:                                  # tail gradients (torch autograd) into the arena
-            if p.grad is not None and p.grad.data_ptr() != arena.gview(n).data_ptr():
-                arena.gview(n).copy_(p.grad)
-        if self.world > 1:
-            dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM)
+        model.engine().stats["grad_hook"] = self._on_grad_stage
+        loss.backward()
+        for w in self.pending:
+            w.wait()
+        self.pending = []
         lib.call("edb_sgd_step", arena.flat.data_ptr(), arena.grad.data_ptr(), self.mom.data_ptr(),
                  arena.flat16.data_ptr(), self.flags.data_ptr(), arena.total, self.lr, self.momentum, self.wd,
                  self.wd_bias, self.blf, 1.0 / self.world, int(self.first), lib.stream_ptr())

@@ -75,21 +75,37 @@ def test_two_rank_allreduce_sgd_matches_reference_recipe(tmp_path):
         assert torch.allclose(got["flat"][o:o + k].view(p.shape), p.detach(), rtol=1e-6, atol=1e-7), n
 
 
-def test_trainer_flags_follow_reference_groups():
-    """train.Trainer marks bias chunks (lr x2), skips the never-used BACKBONE.base.fc.* and the alignment padding."""
+def test_trainer_flags_and_gradient_buckets():
+    """train.Trainer on the real parameter arena (built on CPU): bias chunks get lr x2, the never-used
+    BACKBONE.base.fc.* and alignment padding are skipped, and the allreduce buckets partition the arena in the order the
+    backward completes them."""
+    import __graft_entry__ as ge
+    from editor_b200.engine import Arena
     from editor_b200.train import Trainer
+    model, *_ = ge._small_case(True, 2)
+    arena = Arena(model, torch.device("cpu"))
+    t = Trainer(model)
+    t._setup(arena)
+    flags = t.flags
 
-    class FakeArena:
-        pass
-    a = FakeArena()
-    a.names = ["BACKBONE.base.blocks.0.attn.qkv.weight", "BACKBONE.base.blocks.0.attn.qkv.bias", "BACKBONE.base.fc.weight",
-               "FUSE_HEAD.weight"]
-    a.offsets = {a.names[0]: (0, 100, (100,)), a.names[1]: (128, 10, (10,)), a.names[2]: (192, 64, (64,)),
-                 a.names[3]: (256, 65, (65,))}
-    a.total = 384
-    a.flat = torch.zeros(a.total)
-    a.params = [torch.nn.Parameter(torch.zeros(1)) for _ in a.names]
-    t = Trainer(torch.nn.Linear(1, 1))
-    t._setup(a)
-    assert t.flags.tolist() == [0, 0, 1, 2, 0, 0]
-    assert [n for n, _ in t.tail] == ["FUSE_HEAD.weight"]
+    def chunk_flags(name):
+        o, n, _ = arena.offsets[name]
+        return set(flags[o // 64:(o + n + 63) // 64].tolist())
+    assert chunk_flags("BACKBONE.base.blocks.3.attn.qkv.weight") == {0}
+    assert chunk_flags("BACKBONE.base.blocks.3.attn.qkv.bias") == {1}
+    assert chunk_flags("FUSE_BN.bias") == {1} and chunk_flags("FUSE_BN.weight") == {0}
+    assert chunk_flags("BACKBONE.base.fc.weight") == {2} and chunk_flags("BACKBONE.base.fc.bias") == {2}
+    spans = sorted(t.buckets.values())
+    assert spans[0][0] == 0 and spans[-1][1] == arena.total
+    assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))          # contiguous, no overlap, no hole
+    off = lambda n: arena.offsets[n][0]                                        # noqa: E731
+    lo, hi = t.buckets["after_backbone"]
+    assert all(lo <= off(n) < hi for n in arena.names if not n.startswith("BACKBONE.base."))
+    lo, hi = t.buckets["blocks_from_8"]
+    assert all(lo <= off(n) < hi for n in arena.names if any(n.startswith("BACKBONE.base.blocks.%d." % i) for i in (8, 9, 10, 11)))
+    lo, hi = t.buckets["rest"]
+    assert all(lo <= off(n) < hi for n in ("BACKBONE.base.cls_token", "BACKBONE.base.pos_embed",
+                                           "BACKBONE.base.patch_embed.proj.weight", "BACKBONE.base.blocks.0.mlp.fc2.bias"))
+    # the model still owns its parameters after the arena re-binds their storage
+    sd = model.state_dict()
+    assert sd["BACKBONE.base.pos_embed"].data_ptr() == arena.view("BACKBONE.base.pos_embed").data_ptr()
