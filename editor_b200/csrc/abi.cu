@@ -63,8 +63,11 @@ int edb_embed_assemble(const float* patch_out, const float* cls, const float* po
     return edb::embed_assemble(patch_out, cls, pos, sie, cam, coe, S, B, P, x, ST);
 }
 int edb_embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos,
-                           float* dsie, void* dpatch_bf16, void* stream) {
-    return edb::embed_assemble_bwd(g, S, B, P, cam, coe, dpos, dsie, dpatch_bf16, ST);
+                           float* dsie, void* dpatch, int dpatch_f32, void* stream) {
+    return edb::embed_assemble_bwd(g, S, B, P, cam, coe, dpos, dsie, dpatch, dpatch_f32, ST);
+}
+int edb_gelu_bwd_f32(const float* dh, const float* pre, float* out, size_t n, void* stream) {
+    return edb::gelu_bwd_f32(dh, pre, out, n, ST);
 }
 static bool tc_eligible(const EdbAttnDesc* d) {
     return d->impl == 0 && !d->f32 && d->seq_off == nullptr && d->fixed_len == 129 && d->heads == 12 && d->P != nullptr &&

@@ -44,7 +44,8 @@ int patch_im2col(const float* rgb, const float* ni, const float* ti, int B, int 
 int embed_assemble(const float* patch_out, const float* cls, const float* pos, const float* sie, const long long* cam,
                    float coe, int S, int B, int P, float* x, cudaStream_t st);
 int embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos, float* dsie,
-                       void* dpatch_bf16, cudaStream_t st);
+                       void* dpatch, int dpatch_f32, cudaStream_t st);
+int gelu_bwd_f32(const float* dh, const float* pre, float* out, size_t n, cudaStream_t st);
 int sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned char* flags, size_t n, float lr, float mu,
              float wd, float wd_bias, float bias_lr_factor, float gscale, int first, cudaStream_t st);
 int attention_simple(const EdbAttnDesc& d, bool bwd, cudaStream_t st);

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_fwd_kernel(const AttnA
 
 template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnArgs a) {
+    // Two phases share two shared-memory tiles: phase A holds (K, V) and produces delta_i and dQ_i, one query row per warp;
+    // phase B reloads the tiles with (Q, dO) and produces dK_j, dV_j, one key row per warp (dS column recomputed).
     constexpr int ST = SmemPad<T>::kStride;
     extern __shared__ uint8_t smem_raw[];
     const int s = blockIdx.x / a.H, h = blockIdx.x % a.H;
@@ -129,12 +131,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnA
     const int L = a.seq_off ? a.seq_off[s + 1] - off : a.fixed_len;
     if (L <= 0) return;
     const int ML = a.max_len;
-    T* Qs = reinterpret_cast<T*>(smem_raw);
-    T* Ks = Qs + (size_t)ML * ST;
-    T* Vs = Ks + (size_t)ML * ST;
-    T* Gs = Vs + (size_t)ML * ST;  // dO
-    float* delta = reinterpret_cast<float*>(Gs + (size_t)ML * ST);
-    float* pbuf = delta + ML;      // [WARPS][2][ML]
+    T* T0 = reinterpret_cast<T*>(smem_raw);            // K, then Q
+    T* T1 = T0 + (size_t)ML * ST;                      // V, then dO
+    float* delta = reinterpret_cast<float*>(T1 + (size_t)ML * ST);
+    float* pbuf = delta + ML;                          // [WARPS][2][ML]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T* qkv = reinterpret_cast<const T*>(a.qkv);
     const T* dO = reinterpret_cast<const T*>(a.d_out);
@@ -144,19 +144,17 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnA
     for (int i = threadIdx.x; i < L * HD; i += WARPS * 32) {
         const int r = i / HD, d = i % HD;
         const T* row = qkv + (size_t)(off + r) * a.ld_qkv + h * HD + d;
-        Qs[r * ST + d] = row[0];
-        Ks[r * ST + d] = row[HC];
-        Vs[r * ST + d] = row[2 * HC];
-        Gs[r * ST + d] = dO[(size_t)(off + r) * a.ld_dout + h * HD + d];
+        T0[r * ST + d] = row[HC];
+        T1[r * ST + d] = row[2 * HC];
     }
     __syncthreads();
     float* p1 = pbuf + (size_t)warp * 2 * ML;
     float* p2 = p1 + ML;
-    // phase A: one query row per warp -> delta_i, dQ_i
     for (int i = warp; i < L; i += WARPS) {
         float g[HD];
+        const T* grow = dO + (size_t)(off + i) * a.ld_dout + h * HD;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) g[d] = to_f(Gs[i * ST + d]);
+        for (int d = 0; d < HD; ++d) g[d] = to_f(grow[d]);
         float dsum = 0.f;
         float dp[8], pp[8];
 #pragma unroll
@@ -165,7 +163,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnA
             dp[jj] = 0.f; pp[jj] = 0.f;
             if (j < L) {
                 float acc = 0.f;
-                const T* vr = Vs + j * ST;
+                const T* vr = T1 + j * ST;
 #pragma unroll
                 for (int d = 0; d < HD; ++d) acc += g[d] * to_f(vr[d]);
                 dp[jj] = acc;
@@ -184,8 +182,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnA
         float o0 = 0.f, o1 = 0.f;
         for (int j = 0; j < L; ++j) {
             const float ds = p1[j];
-            o0 += ds * to_f(Ks[j * ST + lane]);
-            o1 += ds * to_f(Ks[j * ST + lane + 32]);
+            o0 += ds * to_f(T0[j * ST + lane]);
+            o1 += ds * to_f(T0[j * ST + lane + 32]);
         }
         T* orow = dqkv + (size_t)(off + i) * a.ld_qkv + h * HD;
         from_f(orow[lane], o0);
@@ -193,16 +191,22 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnA
         __syncwarp();
     }
     __syncthreads();
-    // phase B: one key row per warp -> dK_j, dV_j (dS column recomputed from dO.V_j, P and delta)
+    for (int i = threadIdx.x; i < L * HD; i += WARPS * 32) {
+        const int r = i / HD, d = i % HD;
+        T0[r * ST + d] = qkv[(size_t)(off + r) * a.ld_qkv + h * HD + d];
+        T1[r * ST + d] = dO[(size_t)(off + r) * a.ld_dout + h * HD + d];
+    }
+    __syncthreads();
     for (int j = warp; j < L; j += WARPS) {
         float v[HD];
+        const T* vrow = qkv + (size_t)(off + j) * a.ld_qkv + 2 * HC + h * HD;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) v[d] = to_f(Vs[j * ST + d]);
+        for (int d = 0; d < HD; ++d) v[d] = to_f(vrow[d]);
         for (int ii = 0; ii < 8; ++ii) {
             const int i = ii * 32 + lane;
             if (i < L) {
                 float acc = 0.f;
-                const T* gr = Gs + i * ST;
+                const T* gr = T1 + i * ST;
 #pragma unroll
                 for (int d = 0; d < HD; ++d) acc += v[d] * to_f(gr[d]);
                 const float p = to_f(Pg[(size_t)i * a.ldp + j]);
@@ -214,10 +218,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_simple_bwd_kernel(const AttnA
         float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
         for (int i = 0; i < L; ++i) {
             const float ds = p1[i], p = p2[i];
-            k0 += ds * to_f(Qs[i * ST + lane]);
-            k1 += ds * to_f(Qs[i * ST + lane + 32]);
-            v0 += p * to_f(Gs[i * ST + lane]);
-            v1 += p * to_f(Gs[i * ST + lane + 32]);
+            k0 += ds * to_f(T0[i * ST + lane]);
+            k1 += ds * to_f(T0[i * ST + lane + 32]);
+            v0 += p * to_f(T1[i * ST + lane]);
+            v1 += p * to_f(T1[i * ST + lane + 32]);
         }
         T* krow = dqkv + (size_t)(off + j) * a.ld_qkv + HC + h * HD;
         from_f(krow[lane], k0);
@@ -235,7 +239,7 @@ static int launch_simple(const AttnArgs& a, bool bwd, cudaStream_t st) {
     constexpr int ST = SmemPad<T>::kStride;
     size_t smem;
     if (!bwd) smem = (size_t)2 * a.max_len * ST * sizeof(T) + (size_t)kSimpleWarps * a.max_len * sizeof(float);
-    else smem = (size_t)4 * a.max_len * ST * sizeof(T) + (size_t)(1 + 2 * kSimpleWarps) * a.max_len * sizeof(float);
+    else smem = (size_t)2 * a.max_len * ST * sizeof(T) + (size_t)(1 + 2 * kSimpleWarps) * a.max_len * sizeof(float);
     if (smem > 227 * 1024) return edb_set_error(EDB_ERR_SHAPE, "attention: sequence too long for shared memory");
     auto kern = bwd ? attn_simple_bwd_kernel<T, kSimpleWarps> : attn_simple_fwd_kernel<T, kSimpleWarps>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -294,6 +294,8 @@ int zero_rows(void* base, long long row_bytes, const int* rows_dev, int nrows, c
 // fp32-faithful GEMMs on the bf16 tensor-core kernel: x = h + m + l (three bf16 pieces, 24 mantissa bits); the six
 // products of order <= 2 are obtained from ONE GEMM by concatenating pieces along K:
 //   role 0 (A side): [h | h | m | h | l | m]      role 1 (B side): [h | m | h | l | h | m]
+// roles 2 / 3: the same A- / B-side piece orders concatenated along ROWS (dst is [6*rows][K]) -- operands whose reduction
+// dimension is the row index (MN-major A/B of the dgrad / wgrad products).
 __global__ void split_kernel(const float* __restrict__ src, long long ld, int rows, int K,
                              __nv_bfloat16* __restrict__ dst, int role) {
     const int kq = K / 4;
@@ -310,12 +312,14 @@ __global__ void split_kernel(const float* __restrict__ src, long long ld, int ro
             m[j] = __bfloat162float(__float2bfloat16(r1));
             l[j] = __bfloat162float(__float2bfloat16(r1 - m[j]));
         }
-        __nv_bfloat16* o = dst + (size_t)r * (6 * (size_t)K) + c;
+        const bool by_rows = role >= 2;
+        __nv_bfloat16* o = by_rows ? dst + (size_t)r * K + c : dst + (size_t)r * (6 * (size_t)K) + c;
+        const size_t step = by_rows ? (size_t)rows * K : (size_t)K;
         const float* seq[6];
-        if (role == 0) { seq[0] = h; seq[1] = h; seq[2] = m; seq[3] = h; seq[4] = l; seq[5] = m; }
-        else           { seq[0] = h; seq[1] = m; seq[2] = h; seq[3] = l; seq[4] = h; seq[5] = m; }
+        if ((role & 1) == 0) { seq[0] = h; seq[1] = h; seq[2] = m; seq[3] = h; seq[4] = l; seq[5] = m; }
+        else                 { seq[0] = h; seq[1] = m; seq[2] = h; seq[3] = l; seq[4] = h; seq[5] = m; }
 #pragma unroll
-        for (int t = 0; t < 6; ++t) store4(o + (size_t)t * K, seq[t][0], seq[t][1], seq[t][2], seq[t][3]);
+        for (int t = 0; t < 6; ++t) store4(o + (size_t)t * step, seq[t][0], seq[t][1], seq[t][2], seq[t][3]);
     }
 }
 
@@ -326,6 +330,32 @@ int split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     split_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld, rows, K, (__nv_bfloat16*)dst, role);
+    EDB_CHECK_LAUNCH();
+    return EDB_OK;
+}
+
+// out = dh * gelu'(pre), exact erf (fp32-faithful backward of nn.GELU, vit_pytorch.py:130)
+__global__ void gelu_bwd_f32_kernel(const float* __restrict__ dh, const float* __restrict__ pre, float* __restrict__ out,
+                                    size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 d = load4(dh + i * 4), x = load4(pre + i * 4);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+        float gr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float cdf = 0.5f * (1.0f + erff(xs[j] * 0.70710678118654752f));
+            gr[j] = cdf + xs[j] * 0.3989422804014327f * expf(-0.5f * xs[j] * xs[j]);
+        }
+        store4(out + i * 4, d.x * gr[0], d.y * gr[1], d.z * gr[2], d.w * gr[3]);
+    }
+}
+
+int gelu_bwd_f32(const float* dh, const float* pre, float* out, size_t n, cudaStream_t st) {
+    if (n == 0) return EDB_OK;
+    if (n % 4) return edb_set_error(EDB_ERR_ALIGN, "gelu_bwd: element count must be a multiple of 4");
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+    gelu_bwd_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(dh, pre, out, n / 4);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }
@@ -403,9 +433,9 @@ int embed_assemble(const float* patch_out, const float* cls, const float* pos, c
 }
 
 // backward: dpos[t] += sum_s g[s][t];  dpatch(bf16)[s*P+t-1] = g[s][t];  dsie[cam] += coe * sum_t g[s][t]
+template <typename OutT>
 __global__ void __launch_bounds__(192) embed_bwd_pos_kernel(const float* __restrict__ g, int S, int N,
-                                                            float* __restrict__ dpos,
-                                                            __nv_bfloat16* __restrict__ dpatch) {
+                                                            float* __restrict__ dpos, OutT* __restrict__ dpatch) {
     const int t = blockIdx.x, c = threadIdx.x * 4;
     const int s0 = blockIdx.y, sstep = gridDim.y;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -432,10 +462,11 @@ __global__ void __launch_bounds__(192) embed_bwd_sie_kernel(const float* __restr
 }
 
 int embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos, float* dsie,
-                       void* dpatch_bf16, cudaStream_t st) {
+                       void* dpatch, int dpatch_f32, cudaStream_t st) {
     if (S <= 0) return EDB_OK;
     int ysplit = S < 8 ? S : 8;
-    embed_bwd_pos_kernel<<<dim3(P + 1, ysplit), 192, 0, st>>>(g, S, P + 1, dpos, (__nv_bfloat16*)dpatch_bf16);
+    if (dpatch_f32) embed_bwd_pos_kernel<float><<<dim3(P + 1, ysplit), 192, 0, st>>>(g, S, P + 1, dpos, (float*)dpatch);
+    else embed_bwd_pos_kernel<__nv_bfloat16><<<dim3(P + 1, ysplit), 192, 0, st>>>(g, S, P + 1, dpos, (__nv_bfloat16*)dpatch);
     EDB_CHECK_LAUNCH();
     if (dsie != nullptr) {
         embed_bwd_sie_kernel<<<S, 192, 0, st>>>(g, B, P + 1, cam, coe, dsie);

@@ -54,6 +54,21 @@ class _Lin:
         return self._split
 
 
+    def wsplit_rows(self, pad_rows=None):
+        """[6*out(_padded), in] bf16: the split pieces concatenated along rows -- B operand of the fp32 dgrad."""
+        ver = (self.eng.arena.version(self.wname), self.eng.arena.generation)
+        rows = pad_rows or self.out_f
+        if getattr(self, "_split_r", None) is None or ver != self._split_r_version:
+            src = self.w32
+            if rows != self.out_f:
+                src = torch.zeros(rows, self.in_f, dtype=torch.float32, device=self.w32.device)
+                src[:self.out_f] = self.w32
+            self._split_r = torch.empty(6 * rows, self.in_f, dtype=torch.bfloat16, device=self.w32.device)
+            lib.split3(src, self._split_r, 3)
+            self._split_r_version = ver
+        return self._split_r
+
+
 class _Norm:
     def __init__(self, eng, prefix, eps):
         a = eng.arena
@@ -233,6 +248,48 @@ class EditorEngine:
         split = _pick_split(tiles, (rows + 63) // 64)
         lib.gemm(dy, x, L.gw, L.out_f, L.in_f, rows, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=split, K_dev=rd)
 
+    def _dgrad32(self, dy, L, out, rows):
+        """fp32-faithful dgrad: out[rows, in] = dy[rows, out] @ W  (3-piece bf16 split of both operands)."""
+        ds = self.ws.get("split_a", (dy.shape[0], 6 * L.out_f), torch.bfloat16)
+        lib.split3(dy, ds, 0, rows)
+        lib.gemm(ds, L.wsplit_rows(), out, rows, L.in_f, 6 * L.out_f, b_mn=True)
+
+    def _wgrad32(self, dy, x, L, rows):
+        """fp32-faithful wgrad: dW[out, in] += dy^T x, both operands split along the reduction (row) dimension."""
+        da = self.ws.get("split_ra", (6 * dy.shape[0] * L.out_f,), torch.bfloat16)[:6 * rows * L.out_f].view(6 * rows, L.out_f)
+        xb = self.ws.get("split_rb", (6 * x.shape[0] * L.in_f,), torch.bfloat16)[:6 * rows * L.in_f].view(6 * rows, L.in_f)
+        lib.split3(dy, da, 2, rows)
+        lib.split3(x, xb, 3, rows)
+        tiles = ((L.out_f + 127) // 128) * ((L.in_f + 255) // 256 if L.in_f > 128 else 1)
+        split = _pick_split(tiles, (6 * rows + 63) // 64)
+        lib.gemm(da, xb, L.gw, L.out_f, L.in_f, 6 * rows, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=split)
+
+    def _block_bwd32(self, g, rows, bp, sv, attn_bwd, dcol_prev):
+        """fp32-faithful backward of one block (EDB_PREC_FP32; DROP_PATH must be 0).  g: fp32 gradient w.r.t. the block
+        output, updated in place to the gradient w.r.t. the block input."""
+        ws, cap = self.ws, g.shape[0]
+        dh = ws.get("dh32", (cap, HID), torch.float32)
+        self._dgrad32(g, bp.fc2, dh, rows)
+        dpre = ws.get("dpre32", (cap, HID), torch.float32)
+        lib.call("edb_gelu_bwd_f32", dh.data_ptr(), sv["pre"].data_ptr(), dpre.data_ptr(), rows * HID, lib.stream_ptr())
+        self._wgrad32(g, sv["h"], bp.fc2, rows)
+        if bp.fc1.gb is not None:
+            lib.colsum(dpre, bp.fc1.gb, rows, HID)
+        dln = ws.get("dln32", (cap, DIM), torch.float32)
+        self._dgrad32(dpre, bp.fc1, dln, rows)
+        self._wgrad32(dpre, sv["ln2"], bp.fc1, rows)
+        lib.layernorm_bwd(dln, sv["x1"], sv["m2"], sv["r2"], bp.ln2.g, g, g, None, bp.ln2.gg, bp.ln2.gb, bp.proj.gb, rows)
+        datt = ws.get("datt32", (cap, DIM), torch.float32)
+        self._dgrad32(g, bp.proj, datt, rows)
+        self._wgrad32(g, sv["att"], bp.proj, rows)
+        dqkv = ws.get("dqkv32", (cap, 3 * DIM), torch.float32)
+        attn_bwd(sv["qkv"], sv["P"], datt, dqkv)
+        if bp.qkv.gb is not None:
+            lib.colsum(dqkv, bp.qkv.gb, rows, 3 * DIM)
+        self._dgrad32(dqkv, bp.qkv, dln, rows)
+        self._wgrad32(dqkv, sv["ln1"], bp.qkv, rows)
+        lib.layernorm_bwd(dln, sv["x"], sv["m1"], sv["r1"], bp.ln1.g, g, g, None, bp.ln1.gg, bp.ln1.gb, dcol_prev, rows)
+
     def _block_fwd(self, x, x1, x2, rows, bp, attn, tag, prec, rs_attn=None, rs_mlp=None, group=1, rd=None):
         """One transformer block (vit_pytorch.py:215-220 / :311-317,328-329) on `rows` packed token rows.
         x, x1, x2: fp32 residual stream before / after attention / after MLP.  Returns what the backward needs."""
@@ -329,7 +386,7 @@ class EditorEngine:
         mf, rf = ws.get("bb_mf", (R,), torch.float32), ws.get("bb_rf", (R,), torch.float32)
         lib.layernorm_fwd(x, self.bb_norm.g, self.bb_norm.b, self.bb_norm.eps, tokens.view(R, DIM), mf, rf, R)
         return tokens, dict(blocks=saved, x_last=x, mf=mf, rf=rf, maps=maps, patches=patches, B=B, cam=cam,
-                            droppath=droppath)
+                            droppath=droppath, prec=prec)
 
     def _grad_stage(self, stage):
         """Tell the trainer that a contiguous slice of the gradient arena is final (bucketed allreduce, train.py)."""
@@ -343,6 +400,8 @@ class EditorEngine:
         B = sv["B"]
         S, R = 3 * B, 3 * B * NTOK
         dp = sv["droppath"]
+        if sv["prec"] == FP32:
+            return self._backbone_backward32(sv, d_tokens)
         g = ws.get("g", (R, DIM), torch.float32)
         gb = ws.get("gb", (R, DIM), torch.bfloat16)
         last = self.bb_blocks[-1]
@@ -366,10 +425,39 @@ class EditorEngine:
         dpos = a.gview(base + "pos_embed").view(NTOK, DIM)
         dsie = a.gview(base + "sie_embed") if (base + "sie_embed") in a.offsets else None
         lib.call("edb_embed_assemble_bwd", g.data_ptr(), S, B, NPATCH, sv["cam"].data_ptr(), self.model.sie_coe,
-                 dpos.data_ptr(), lib.ptr(dsie), dpatch.data_ptr(), lib.stream_ptr())
+                 dpos.data_ptr(), lib.ptr(dsie), dpatch.data_ptr(), 0, lib.stream_ptr())
         a.gview(base + "cls_token").view(DIM).add_(dpos[0])
         lib.colsum(dpos[1:], self.patch.gb, NPATCH, DIM)
         self._wgrad(dpatch, sv["patches"], self.patch, S * NPATCH)
+        self._grad_stage("rest")
+
+    def _backbone_backward32(self, sv, d_tokens):
+        ws, a = self.ws, self.arena
+        B = sv["B"]
+        S, R = 3 * B, 3 * B * NTOK
+        if sv["droppath"] is not None:
+            raise lib.EdbError("the fp32-faithful backward supports MODEL.DROP_PATH 0.0 only")
+        g = ws.get("g", (R, DIM), torch.float32)
+        lib.layernorm_bwd(d_tokens.reshape(R, DIM), sv["x_last"], sv["mf"], sv["rf"], self.bb_norm.g, None, g, None,
+                          self.bb_norm.gg, self.bb_norm.gb, self.bb_blocks[-1].fc2.gb, R)
+
+        def attn_bwd(qkv, P, datt, dqkv):
+            lib.attention(qkv, None, P, S, HEADS, NTOK, SCALE, fixed_len=NTOK, p_rows=NTOK, ldp=P_LD, impl=1, d_out=datt,
+                          d_qkv=dqkv, backward=True)
+        for l in range(11, -1, -1):
+            prev_gb = self.bb_blocks[l - 1].fc2.gb if l > 0 else None
+            self._block_bwd32(g, R, self.bb_blocks[l], sv["blocks"][l], attn_bwd, prev_gb)
+            if l in (8, 4):
+                self._grad_stage("blocks_from_%d" % l)
+        base = "BACKBONE.base."
+        dpatch = ws.get("dpatch32", (S * NPATCH, DIM), torch.float32)
+        dpos = a.gview(base + "pos_embed").view(NTOK, DIM)
+        dsie = a.gview(base + "sie_embed") if (base + "sie_embed") in a.offsets else None
+        lib.call("edb_embed_assemble_bwd", g.data_ptr(), S, B, NPATCH, sv["cam"].data_ptr(), self.model.sie_coe,
+                 dpos.data_ptr(), lib.ptr(dsie), dpatch.data_ptr(), 1, lib.stream_ptr())
+        a.gview(base + "cls_token").view(DIM).add_(dpos[0])
+        lib.colsum(dpos[1:], self.patch.gb, NPATCH, DIM)
+        self._wgrad32(dpatch, sv["patches"], self.patch, S * NPATCH)
         self._grad_stage("rest")
 
     # ------------------------------------------------------------------ SFTS selection (no gradient)
@@ -400,6 +488,11 @@ class EditorEngine:
         ml_cap = min(NTOK, 1 + 3 * HEADS * int(m.head_keep) + int(m.FREQ_INDEX.keep))
         sel = dict(index=index, seq_off=seq_off, seq_off3=seq_off3, B=B, ml_cap=ml_cap, T_cap=B * ml_cap,
                    T_dev=seq_off.data_ptr() + 4 * B, T3_dev=seq_off3.data_ptr() + 4 * B, debug=dbg)
+        if prec == FP32:
+            # parity mode: exact row counts on the host (one sync, like make_model.py:200); the split operands of the
+            # fp32-faithful GEMMs are laid out by the actual row count
+            off_host = seq_off.cpu()
+            sel.update(T_cap=int(off_host[-1]), ml_cap=int((off_host[1:] - off_host[:-1]).max()), T_dev=None, T3_dev=None)
         return sel
 
     # ------------------------------------------------------------------ HMA on packed kept tokens
@@ -466,7 +559,7 @@ class EditorEngine:
         num = torch.empty(B, dtype=torch.int32, device=dev)
         lib.call("edb_pool_fwd", xo.data_ptr(), sel["seq_off"].data_ptr(), B, cls_out.data_ptr(), patch_mean.data_ptr(),
                  num.data_ptr(), lib.stream_ptr())
-        sv = dict(mods=saved, joint=svj, xj2=xj2, mo=mo, ro=ro, num=num, abwd=abwd, jbwd=jbwd, cap=cap)
+        sv = dict(mods=saved, joint=svj, xj2=xj2, mo=mo, ro=ro, num=num, abwd=abwd, jbwd=jbwd, cap=cap, prec=prec)
         return cls_out, patch_mean, cls_mid, loss_bcc, num, sv
 
     def hma_backward(self, tokens, sel, sv, d_cls, d_patch, d_mid, d_bcc):
@@ -477,18 +570,25 @@ class EditorEngine:
         lib.call("edb_pool_bwd", d_cls.data_ptr(), d_patch.data_ptr(), sel["seq_off"].data_ptr(), sv["num"].data_ptr(), B,
                  ml, dxo.data_ptr(), lib.stream_ptr())
         gj = ws.get("hma_gj", (3 * cap, DIM), torch.float32)
-        gbj = ws.get("hma_gbj", (3 * cap + 64, DIM), torch.bfloat16)
+        fp32 = sv["prec"] == FP32
+        gbj = None if fp32 else ws.get("hma_gbj", (3 * cap + 64, DIM), torch.bfloat16)
         lib.layernorm_bwd(dxo, sv["xj2"], sv["mo"], sv["ro"], self.hma_out.g, None, gj, gbj, self.hma_out.gg,
                           self.hma_out.gb, None, 3 * T, rows_dev=t3d)
-        self._block_bwd(gj, gbj, 3 * T, self.hma_blocks[3], sv["joint"], sv["jbwd"], None, rd=t3d)
+        if fp32:
+            self._block_bwd32(gj, 3 * T, self.hma_blocks[3], sv["joint"], sv["jbwd"], None)
+        else:
+            self._block_bwd(gj, gbj, 3 * T, self.hma_blocks[3], sv["joint"], sv["jbwd"], None, rd=t3d)
         gm = ws.get("hma_gm", (3, cap, DIM), torch.float32)
         lib.call("edb_joint_gather", gm.data_ptr(), cap, gj.data_ptr(), sel["seq_off"].data_ptr(), B, ml, 1,
                  lib.stream_ptr())
         if d_mid is not None:
             lib.call("edb_cls_rows", gm.data_ptr(), cap, sel["seq_off"].data_ptr(), B, d_mid.data_ptr(), 1,
                      lib.stream_ptr())
-        gbm = ws.get("hma_gbm", (cap + 64, DIM), torch.bfloat16)
+        gbm = None if fp32 else ws.get("hma_gbm", (cap + 64, DIM), torch.bfloat16)
         for m in range(3):
+            if fp32:
+                self._block_bwd32(gm[m], T, self.hma_blocks[m], sv["mods"][m], sv["abwd"], None)
+                continue
             lib.call("edb_cast_rows_f32_bf16", gm[m].data_ptr(), gbm.data_ptr(), T, DIM, td, lib.stream_ptr())
             self._block_bwd(gm[m], gbm, T, self.hma_blocks[m], sv["mods"][m], sv["abwd"], None, rd=td)
         d_tokens = torch.empty_like(tokens)
@@ -531,8 +631,8 @@ class EditorEngine:
         cam = cam_label.to(torch.int64).contiguous()
         training = m.training
         prec = self._precision(training)
-        # training forward also runs fp32-faithful (model.precision = "fp32"): outputs / loss / selection to 1e-3 of the
-        # reference; its backward is not implemented (the autograd Functions raise)
+        # model.precision = "fp32" trains fp32-faithfully (every GEMM as a 3-piece bf16 split, fp32 attention): the parity
+        # mode of BASELINE.json configs[4]; ~6x the tensor work of the bf16 mode
         self.arena.refresh16()
         if not training:
             with torch.no_grad():
@@ -585,8 +685,6 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_tokens):
         eng = ctx.eng
-        if ctx.prec != BF16:
-            raise lib.EdbError("backward is implemented for the bf16 tensor-core mode only")
         eng._mark("bb_bwd_start")
         eng.backbone_backward(ctx.sv, d_tokens.contiguous().float())
         eng._mark("bb_bwd_end")
@@ -608,8 +706,6 @@ class _HMAFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_cls, d_patch, d_mid, d_bcc):
         eng = ctx.eng
-        if ctx.prec != BF16:
-            raise lib.EdbError("backward is implemented for the bf16 tensor-core mode only")
         (tokens,) = ctx.saved_tensors
         z = lambda t, ref: torch.zeros_like(ref) if t is None else t.contiguous().float()   # noqa: E731
         shape_ref = torch.empty(3, ctx.sel["B"], DIM, device=tokens.device)

@@ -71,7 +71,8 @@ SIGNATURES = {
     "edb_split_bf16x3": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_int, c_vp]),
     "edb_patch_im2col": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp]),
     "edb_embed_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_int, c_int, c_int, c_vp, c_vp]),
-    "edb_embed_assemble_bwd": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_float, c_vp, c_vp, c_vp, c_vp]),
+    "edb_embed_assemble_bwd": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_float, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "edb_gelu_bwd_f32": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp]),
     "edb_attention_fwd": (c_int, [ctypes.POINTER(AttnDesc), c_vp]),
     "edb_attention_bwd": (c_int, [ctypes.POINTER(AttnDesc), c_vp]),
     "edb_freq_counts": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
@@ -207,7 +208,7 @@ def cast_bf16(src, dst, n=None):
 
 
 def split3(src, dst, role, rows=None):
-    """src fp32 [rows,K] -> dst bf16 [rows, 6K] (role 0 = A side, 1 = B side)."""
+    """src fp32 [rows,K] -> dst bf16 [rows, 6K] (role 0 = A side, 1 = B side) or [6*rows, K] (roles 2 / 3)."""
     call("edb_split_bf16x3", src.data_ptr(), src.stride(0), src.shape[0] if rows is None else rows, src.shape[1],
          dst.data_ptr(), role, stream_ptr())
     return dst

@@ -28,22 +28,31 @@ class LinearFn(torch.autograd.Function):
             xb = torch.empty(B, 6 * K, dtype=torch.bfloat16, device=x.device)
             lib.split3(x, xb, 0)
             lib.gemm(xb, L.wsplit(), y, B, N, 6 * K, bias=L.b)
-        ctx.eng, ctx.L, ctx.xb, ctx.prec = eng, L, xb, prec
+        ctx.eng, ctx.L, ctx.xb, ctx.prec, ctx.x32 = eng, L, xb, prec, (x if prec != BF16 else None)
         return y[:, :N]
 
     @staticmethod
     def backward(ctx, dy):
         eng, L, xb = ctx.eng, ctx.L, ctx.xb
-        if ctx.prec != BF16:
-            raise lib.EdbError("backward is implemented for the bf16 mode only")
         B, K, N = dy.shape[0], L.in_f, L.out_f
-        dyf = torch.zeros(B, _pad8(N), dtype=torch.float32, device=dy.device)
+        Np = _pad8(N)
+        dyf = torch.zeros(B, Np, dtype=torch.float32, device=dy.device)
         dyf[:, :N] = dy
-        dyb = torch.empty(B, _pad8(N), dtype=torch.bfloat16, device=dy.device)
-        lib.cast_bf16(dyf, dyb)
         dx = torch.empty(B, K, dtype=torch.float32, device=dy.device)
-        lib.gemm(dyb, L.w16, dx, B, K, N, b_mn=True)
-        lib.gemm(dyb, xb, L.gw, N, K, B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
+        if ctx.prec == BF16:
+            dyb = torch.empty(B, Np, dtype=torch.bfloat16, device=dy.device)
+            lib.cast_bf16(dyf, dyb)
+            lib.gemm(dyb, L.w16, dx, B, K, N, b_mn=True)
+            lib.gemm(dyb, xb, L.gw, N, K, B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
+        else:       # fp32-faithful: 3-piece splits along the reduction dimension of each product
+            ds = torch.empty(B, 6 * Np, dtype=torch.bfloat16, device=dy.device)
+            lib.split3(dyf, ds, 0)
+            lib.gemm(ds, L.wsplit_rows(Np), dx, B, K, 6 * Np, b_mn=True)
+            da = torch.empty(6 * B, Np, dtype=torch.bfloat16, device=dy.device)
+            xr = torch.empty(6 * B, K, dtype=torch.bfloat16, device=dy.device)
+            lib.split3(dyf, da, 2)
+            lib.split3(ctx.x32, xr, 3)
+            lib.gemm(da, xr, L.gw, N, K, 6 * B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
         names = {L.wname}
         if L.gb is not None:
             lib.colsum(dyf, L.gb, B, N)

@@ -1,6 +1,6 @@
 """Training step around the hot path: loss (layers/make_loss.py:36-56 as called by engine/processor.py:82-92), one
 gradient allreduce over the flat arena (the one collective of the path, processor.py:47-50) and the fused SGD-momentum
-update (solver/make_optimizer.py:6-22).  Rows f-1 / f-2 of SURVEY.md section 8: the loss is still plain torch ops."""
+update (solver/make_optimizer.py:6-22).  Rows f-1 / f-2 of SURVEY.md section 8."""
 import torch
 import torch.distributed as dist
 

@@ -106,7 +106,8 @@ int edb_sgd_step(float* p, const float* g, float* buf, void* p16, const unsigned
                  float momentum, float wd, float wd_bias, float bias_lr_factor, float gscale, int first, void* stream);
 
 /* fp32 -> 3-piece bf16 split laid out along K for the fp32-faithful GEMM: dst is [rows][6*K] bf16;
- * role 0 = A-side order, role 1 = B-side order (see rowops.cu).  EDB_PREC_FP32 path only. */
+ * role 0 = A-side order, role 1 = B-side order; roles 2 / 3: the same orders concatenated along rows, dst [6*rows][K]
+ * (operands whose reduction dimension is the row index: dgrad weights, wgrad activations).  EDB_PREC_FP32 path only. */
 int edb_split_bf16x3(const float* src, long long ld, int rows, int K, void* dst, int role, void* stream);
 
 /* patches[(m*B+b)*P + p][c*256+ky*16+kx] of the three modality images [B,3,H,W]: the k16/s16 patch conv as a GEMM
@@ -118,9 +119,11 @@ int edb_patch_im2col(const float* rgb, const float* ni, const float* ti, int B, 
  * sie may be NULL.  cam is int64[B]. */
 int edb_embed_assemble(const float* patch_out, const float* cls, const float* pos, const float* sie,
                        const long long* cam, float coe, int S, int B, int P, float* x, void* stream);
-/* dpos += sum_s g;  dsie[cam] += coe*sum_t g;  dpatch (bf16, [S*P][768]) = g[:,1:]  */
+/* dpos += sum_s g;  dsie[cam] += coe*sum_t g;  dpatch (bf16 or fp32, [S*P][768]) = g[:,1:]  */
 int edb_embed_assemble_bwd(const float* g, int S, int B, int P, const long long* cam, float coe, float* dpos,
-                           float* dsie, void* dpatch_bf16, void* stream);
+                           float* dsie, void* dpatch, int dpatch_f32, void* stream);
+/* out = dh * gelu'(pre) with exact erf: backward of nn.GELU in the fp32-faithful mode (vit_pytorch.py:130,139-145) */
+int edb_gelu_bwd_f32(const float* dh, const float* pre, float* out, size_t n, void* stream);
 
 /* ---- attention ---------------------------------------------------------------------------------------------- */
 

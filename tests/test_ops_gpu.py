@@ -105,7 +105,7 @@ def test_patch_embed_matches_conv(H, W):
     dpos, dsie = torch.zeros(129, 768, device="cuda"), torch.zeros(4, 768, device="cuda")
     dpatch = torch.empty(3 * B * 128, 768, dtype=torch.bfloat16, device="cuda")
     lib.call("edb_embed_assemble_bwd", g.data_ptr(), 3 * B, B, 128, cam.data_ptr(), 3.0, dpos.data_ptr(), dsie.data_ptr(),
-             dpatch.data_ptr(), lib.stream_ptr())
+             dpatch.data_ptr(), 0, lib.stream_ptr())
     assert _rel(dpos, g.sum(0)) < 1e-5
     want_sie = torch.zeros(4, 768, device="cuda").index_add_(0, cam.repeat(3), 3.0 * g.sum(1))
     assert _rel(dsie, want_sie) < 1e-5
@@ -144,8 +144,6 @@ def test_attention_cuda_core_fwd_bwd(dtype, lens):
     for s, L in enumerate(lens):
         got = P.view(len(lens), H, ml, ldp)[s, :, :L, :L].float()
         assert _rel(got, maps[s].detach()) < tol
-    if dtype == torch.float32 and ml > 129:
-        return          # the fp32 backward is not a product path; its shared-memory tiles stop at 129 tokens
     d_out = torch.randn(T, H * 64, generator=_g(2)).cuda().to(dtype)
     ref.backward(d_out.float())
     d_qkv = torch.empty_like(qkv)
