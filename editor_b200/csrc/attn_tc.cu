@@ -13,6 +13,15 @@
 
 namespace edb {
 
+__device__ __forceinline__ float2 lds_bf162(uint32_t addr) {
+    const uint32_t u = lds32(addr);
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ float lds_bf16(uint32_t addr) {
+    const unsigned short u = lds16(addr);
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+}
+
 constexpr int AT_L = 129;       // tokens per sequence
 constexpr int AT_KP = 144;      // keys padded to a multiple of 16
 constexpr int AT_PLD = 136;     // pitch of P in HBM
@@ -122,7 +131,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 acc = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(sK + sw128(j, c));
+                    const uint4 u = lds128(smem_u32(sK) + sw128(j, c));
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -160,8 +169,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int t = 0; t < jn; ++t) {
                 const int j = jj * 32 + t;
                 const float pj = __shfl_sync(0xffffffffu, sc[jj], t);
-                const float2 f = __bfloat1622float2(
-                    *reinterpret_cast<const __nv_bfloat162*>(sV + sw128(j, lane >> 2) + (lane & 3) * 4));
+                const float2 f = lds_bf162(smem_u32(sV) + sw128(j, lane >> 2) + (lane & 3) * 4);
                 o0 += pj * f.x;
                 o1 += pj * f.y;
             }
@@ -215,7 +223,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
                 w[t] = *reinterpret_cast<uint32_t*>(&hb);
             }
-            *reinterpret_cast<uint4*>(sP + (q8 >> 3) * AT_CHUNK_P + sw128(i, q8 & 7)) = u;
+            sts128(smem_u32(sP) + (q8 >> 3) * AT_CHUNK_P + sw128(i, q8 & 7), u);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_p);
@@ -343,7 +351,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
     for (int t = threadIdx.x; t < 5 * 15 * 8; t += 224) {
         const int tile = t / 120, rem = t % 120, line = 129 + rem / 8, c = rem % 8;
         uint8_t* base = tile == 0 ? sQ : (tile == 1 ? sdO : sP + (tile - 2) * BT_TILE);
-        *reinterpret_cast<uint4*>(base + line * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+        sts128(smem_u32(base) + line * 128 + c * 16, make_uint4(0u, 0u, 0u, 0u));
     }
     fence_proxy_async_smem();
     if (warp == 4) {
@@ -418,7 +426,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         float g[AT_HD];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 u = *reinterpret_cast<const uint4*>(sdO + sw128(128, c));
+            const uint4 u = lds128(smem_u32(sdO) + sw128(128, c));
             const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -435,7 +443,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             if (j < AT_KP) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(sV + sw128(j, c));
+                    const uint4 u = lds128(smem_u32(sV) + sw128(j, c));
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -443,8 +451,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                         acc += g[c * 8 + 2 * t] * f.x + g[c * 8 + 2 * t + 1] * f.y;
                     }
                 }
-                pv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                    sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2));
+                pv = lds_bf16(smem_u32(sP) + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2);
                 if (pv == 0.f) acc = 0.f;       // padded keys: garbage V rows must not leak through 0 * inf
             }
             ds[jj] = acc;                        // dP_0j for now
@@ -458,11 +465,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         for (int jj = 0; jj < 5; ++jj) {
             const int j = jj * 32 + lane;
             if (j < AT_KP) {
-                __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) +
-                                                                      (j & 7) * 2);
-                const float pv = __bfloat162float(*ptr);
+                const uint32_t pa = smem_u32(sP) + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2;
+                const float pv = lds_bf16(pa);
                 const __nv_bfloat16 d16 = __float2bfloat16(pv * (ds[jj] - dsum) * p.scale);
-                *ptr = d16;
+                sts16(pa, *reinterpret_cast<const unsigned short*>(&d16));
                 ds[jj] = __bfloat162float(d16);
             } else {
                 ds[jj] = 0.f;
@@ -478,8 +484,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             for (int t = 0; t < jn; ++t) {
                 const int j = jj * 32 + t;
                 const float dj = __shfl_sync(0xffffffffu, ds[jj], t);
-                const float2 f = __bfloat1622float2(
-                    *reinterpret_cast<const __nv_bfloat162*>(sK + sw128(j, lane >> 2) + (lane & 3) * 4));
+                const float2 f = lds_bf162(smem_u32(sK) + sw128(j, lane >> 2) + (lane & 3) * 4);
                 o0 += dj * f.x;
                 o1 += dj * f.y;
             }
@@ -493,7 +498,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int i = ii * 32 + lane;        // query line
-            col[ii] = i < AT_L ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sP + 2 * BT_TILE + sw128(i, 0))) : 0.f;
+            col[ii] = i < AT_L ? lds_bf16(smem_u32(sP) + 2 * BT_TILE + sw128(i, 0)) : 0.f;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pcol);
@@ -504,8 +509,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             for (int t = 0; t < in; ++t) {
                 const int i = ii * 32 + t;
                 const float pj = __shfl_sync(0xffffffffu, col[ii], t);
-                const float2 f = __bfloat1622float2(
-                    *reinterpret_cast<const __nv_bfloat162*>(sdO + sw128(i, lane >> 2) + (lane & 3) * 4));
+                const float2 f = lds_bf162(smem_u32(sdO) + sw128(i, lane >> 2) + (lane & 3) * 4);
                 o0 += pj * f.x;
                 o1 += pj * f.y;
             }
@@ -516,7 +520,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int i = ii * 32 + lane;
-            col[ii] = i < AT_L ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sP + 2 * BT_TILE + sw128(i, 0))) : 0.f;
+            col[ii] = i < AT_L ? lds_bf16(smem_u32(sP) + 2 * BT_TILE + sw128(i, 0)) : 0.f;
         }
         o0 = o1 = 0.f;
 #pragma unroll
@@ -525,8 +529,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             for (int t = 0; t < in; ++t) {
                 const int i = ii * 32 + t;
                 const float dj = __shfl_sync(0xffffffffu, col[ii], t);
-                const float2 f = __bfloat1622float2(
-                    *reinterpret_cast<const __nv_bfloat162*>(sQ + sw128(i, lane >> 2) + (lane & 3) * 4));
+                const float2 f = lds_bf162(smem_u32(sQ) + sw128(i, lane >> 2) + (lane & 3) * 4);
                 o0 += dj * f.x;
                 o1 += dj * f.y;
             }
@@ -549,7 +552,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             const int nq = c < 4 ? 4 : 2;
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
-                const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                const uint4 u = lds128(smem_u32(sP) + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
                 const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -570,8 +573,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             const int nq = c < 4 ? 4 : 2;
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
-                uint4* ptr = reinterpret_cast<uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
-                uint4 u = *ptr;
+                const uint32_t pa = smem_u32(sP) + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q);
+                uint4 u = lds128(pa);
                 __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -580,7 +583,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                     const float b = f.y != 0.f ? f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale : 0.f;
                     hh[t] = __floats2bfloat162_rn(a, b);
                 }
-                *ptr = u;
+                sts128(pa, u);
             }
         }
         fence_proxy_async_smem();

@@ -161,7 +161,7 @@ attn_var_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         w[t] = *reinterpret_cast<uint32_t*>(&hb);
                     }
                 }
-                *reinterpret_cast<uint4*>(sP + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q)) = u;
+                sts128(smem_u32(sP) + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q), u);
             }
         }
         fence_proxy_async_smem();
@@ -293,7 +293,7 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q));
+                    const uint4 u = lds128(smem_u32(sP) + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q));
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -310,8 +310,8 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint4* ptr = reinterpret_cast<uint4*>(sP + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q));
-                    uint4 u = *ptr;
+                    const uint32_t pa = smem_u32(sP) + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q);
+                    uint4 u = lds128(pa);
                     __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -320,7 +320,7 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         const float b = f.y != 0.f ? f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale : 0.f;
                         hh[t] = __floats2bfloat162_rn(a, b);
                     }
-                    *ptr = u;
+                    sts128(pa, u);
                 }
             }
             tc_fence_before();

@@ -281,7 +281,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr int NCH = BN / 64;           // 32-column chunks per warp
         constexpr bool kAuxF32 = (EPI == EPI_RESIDUAL);
         constexpr bool kAuxBf16 = (EPI == EPI_GELU_BWD);
-        uint8_t* stg = smem + S::kStagingOffset + ew * 4096;
+        const uint32_t stg = smem_u32(smem + S::kStagingOffset + ew * 4096);
         const int lrow = lane >> 3;            // phase B: row within a group of 4
         const int lc4 = lane & 7;              // phase B: which float4 of the 32-column chunk
         int acc = 0;
@@ -353,17 +353,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
                 __syncwarp();
                 // ---- phase B
                 if (nvalid > 0) {
                     const bool vD = vec && (p.ldd % 4 == 0), v2 = vec && (p.ld_out2 % 4 == 0);
-#pragma unroll
+                    // static register indexing of the prefetched aux operand needs the full unroll; the other
+                    // epilogues keep the loop rolled up (instruction-cache footprint)
+#pragma unroll(kAuxF32 || kAuxBf16 ? 8 : 2)
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + lrow;
                         const int row = row_base + rr;
-                        float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
+                        const uint4 raw = lds128(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
+                        float4 v = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
+                                               __uint_as_float(raw.w));
                         if (row >= M_rt) continue;
                         v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
                         v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
