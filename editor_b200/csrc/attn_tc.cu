@@ -13,14 +13,10 @@
 
 namespace edb {
 
-__device__ __forceinline__ float2 lds_bf162(uint32_t addr) {
-    const uint32_t u = lds32(addr);
-    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+__device__ __forceinline__ float2 lds_bf162(const uint8_t* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
 }
-__device__ __forceinline__ float lds_bf16(uint32_t addr) {
-    const unsigned short u = lds16(addr);
-    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
-}
+__device__ __forceinline__ float lds_bf16(const uint8_t* p) { return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)); }
 
 constexpr int AT_L = 129;       // tokens per sequence
 constexpr int AT_KP = 144;      // keys padded to a multiple of 16
@@ -46,8 +42,8 @@ struct AttnTcParams {
 __global__ void __launch_bounds__(192, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                    const __grid_constant__ CUtensorMap map_p, const AttnTcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need a 1024-byte aligned base
+    uint8_t* smem = smem_raw;
     uint8_t* sQ = smem + AT_F_SQ;
     uint8_t* sK = smem + AT_F_SK;
     uint8_t* sV = smem + AT_F_SV;
@@ -131,7 +127,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 acc = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 u = lds128(smem_u32(sK) + sw128(j, c));
+                    const uint4 u = *reinterpret_cast<const uint4*>(sK + sw128(j, c));
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -169,7 +165,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int t = 0; t < jn; ++t) {
                 const int j = jj * 32 + t;
                 const float pj = __shfl_sync(0xffffffffu, sc[jj], t);
-                const float2 f = lds_bf162(smem_u32(sV) + sw128(j, lane >> 2) + (lane & 3) * 4);
+                const float2 f = lds_bf162(sV + sw128(j, lane >> 2) + (lane & 3) * 4);
                 o0 += pj * f.x;
                 o1 += pj * f.y;
             }
@@ -223,7 +219,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
                 w[t] = *reinterpret_cast<uint32_t*>(&hb);
             }
-            sts128(smem_u32(sP) + (q8 >> 3) * AT_CHUNK_P + sw128(i, q8 & 7), u);
+            *reinterpret_cast<uint4*>(sP + (q8 >> 3) * AT_CHUNK_P + sw128(i, q8 & 7)) = u;
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_p);
@@ -329,8 +325,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                    const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_do128,
                    const __grid_constant__ CUtensorMap map_do1, const __grid_constant__ CUtensorMap map_p128,
                    const __grid_constant__ CUtensorMap map_p1, const AttnTcBwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need a 1024-byte aligned base
+    uint8_t* smem = smem_raw;
     uint8_t* sQ = smem + BT_SQ;
     uint8_t* sK = smem + BT_SK;
     uint8_t* sV = smem + BT_SV;
@@ -351,7 +347,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
     for (int t = threadIdx.x; t < 5 * 15 * 8; t += 224) {
         const int tile = t / 120, rem = t % 120, line = 129 + rem / 8, c = rem % 8;
         uint8_t* base = tile == 0 ? sQ : (tile == 1 ? sdO : sP + (tile - 2) * BT_TILE);
-        sts128(smem_u32(base) + line * 128 + c * 16, make_uint4(0u, 0u, 0u, 0u));
+        *reinterpret_cast<uint4*>(base + line * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();
     if (warp == 4) {
@@ -426,7 +422,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         float g[AT_HD];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 u = lds128(smem_u32(sdO) + sw128(128, c));
+            const uint4 u = *reinterpret_cast<const uint4*>(sdO + sw128(128, c));
             const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -443,7 +439,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             if (j < AT_KP) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint4 u = lds128(smem_u32(sV) + sw128(j, c));
+                    const uint4 u = *reinterpret_cast<const uint4*>(sV + sw128(j, c));
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -451,7 +447,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                         acc += g[c * 8 + 2 * t] * f.x + g[c * 8 + 2 * t + 1] * f.y;
                     }
                 }
-                pv = lds_bf16(smem_u32(sP) + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2);
+                pv = lds_bf16(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2);
                 if (pv == 0.f) acc = 0.f;       // padded keys: garbage V rows must not leak through 0 * inf
             }
             ds[jj] = acc;                        // dP_0j for now
@@ -465,10 +461,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         for (int jj = 0; jj < 5; ++jj) {
             const int j = jj * 32 + lane;
             if (j < AT_KP) {
-                const uint32_t pa = smem_u32(sP) + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2;
-                const float pv = lds_bf16(pa);
+                __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2);
+                const float pv = __bfloat162float(*pa);
                 const __nv_bfloat16 d16 = __float2bfloat16(pv * (ds[jj] - dsum) * p.scale);
-                sts16(pa, *reinterpret_cast<const unsigned short*>(&d16));
+                *pa = d16;
                 ds[jj] = __bfloat162float(d16);
             } else {
                 ds[jj] = 0.f;
@@ -484,7 +480,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             for (int t = 0; t < jn; ++t) {
                 const int j = jj * 32 + t;
                 const float dj = __shfl_sync(0xffffffffu, ds[jj], t);
-                const float2 f = lds_bf162(smem_u32(sK) + sw128(j, lane >> 2) + (lane & 3) * 4);
+                const float2 f = lds_bf162(sK + sw128(j, lane >> 2) + (lane & 3) * 4);
                 o0 += dj * f.x;
                 o1 += dj * f.y;
             }
@@ -498,7 +494,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int i = ii * 32 + lane;        // query line
-            col[ii] = i < AT_L ? lds_bf16(smem_u32(sP) + 2 * BT_TILE + sw128(i, 0)) : 0.f;
+            col[ii] = i < AT_L ? lds_bf16(sP + 2 * BT_TILE + sw128(i, 0)) : 0.f;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_pcol);
@@ -509,7 +505,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             for (int t = 0; t < in; ++t) {
                 const int i = ii * 32 + t;
                 const float pj = __shfl_sync(0xffffffffu, col[ii], t);
-                const float2 f = lds_bf162(smem_u32(sdO) + sw128(i, lane >> 2) + (lane & 3) * 4);
+                const float2 f = lds_bf162(sdO + sw128(i, lane >> 2) + (lane & 3) * 4);
                 o0 += pj * f.x;
                 o1 += pj * f.y;
             }
@@ -520,7 +516,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int i = ii * 32 + lane;
-            col[ii] = i < AT_L ? lds_bf16(smem_u32(sP) + 2 * BT_TILE + sw128(i, 0)) : 0.f;
+            col[ii] = i < AT_L ? lds_bf16(sP + 2 * BT_TILE + sw128(i, 0)) : 0.f;
         }
         o0 = o1 = 0.f;
 #pragma unroll
@@ -529,7 +525,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             for (int t = 0; t < in; ++t) {
                 const int i = ii * 32 + t;
                 const float dj = __shfl_sync(0xffffffffu, col[ii], t);
-                const float2 f = lds_bf162(smem_u32(sQ) + sw128(i, lane >> 2) + (lane & 3) * 4);
+                const float2 f = lds_bf162(sQ + sw128(i, lane >> 2) + (lane & 3) * 4);
                 o0 += dj * f.x;
                 o1 += dj * f.y;
             }
@@ -552,7 +548,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             const int nq = c < 4 ? 4 : 2;
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
-                const uint4 u = lds128(smem_u32(sP) + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
                 const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -573,8 +569,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             const int nq = c < 4 ? 4 : 2;
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
-                const uint32_t pa = smem_u32(sP) + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q);
-                uint4 u = lds128(pa);
+                uint4* pa = reinterpret_cast<uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                uint4 u = *pa;
                 __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -583,7 +579,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                     const float b = f.y != 0.f ? f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale : 0.f;
                     hh[t] = __floats2bfloat162_rn(a, b);
                 }
-                sts128(pa, u);
+                *pa = u;
             }
         }
         fence_proxy_async_smem();

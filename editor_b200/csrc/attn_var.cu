@@ -62,8 +62,8 @@ attn_var_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const int L = p.seq_off[s + 1] - off;
     if (qt * 128 >= L) return;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need a 1024-byte aligned base
+    uint8_t* smem = smem_raw;
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + AV_QTILE;
     uint8_t* sV = sK + KV_BYTES;
@@ -161,7 +161,7 @@ attn_var_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         w[t] = *reinterpret_cast<uint32_t*>(&hb);
                     }
                 }
-                sts128(smem_u32(sP) + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q), u);
+                *reinterpret_cast<uint4*>(sP + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q)) = u;
             }
         }
         fence_proxy_async_smem();
@@ -192,8 +192,8 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (L <= 0) return;
     const int nqt = (L + 127) >> 7;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need a 1024-byte aligned base
+    uint8_t* smem = smem_raw;
     uint8_t* sQ = smem;
     uint8_t* sdO = sQ + AV_QTILE;
     uint8_t* sK = sdO + AV_QTILE;
@@ -293,7 +293,7 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint4 u = lds128(smem_u32(sP) + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q));
+                    const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q));
                     const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -310,8 +310,8 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint32_t pa = smem_u32(sP) + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q);
-                    uint4 u = lds128(pa);
+                    uint4* pa = reinterpret_cast<uint4*>(sP + (c >> 1) * AV_QTILE + sw128(i, (c & 1) * 4 + q));
+                    uint4 u = *pa;
                     __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -320,7 +320,7 @@ attn_var_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         const float b = f.y != 0.f ? f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale : 0.f;
                         hh[t] = __floats2bfloat162_rn(a, b);
                     }
-                    sts128(pa, u);
+                    *pa = u;
                 }
             }
             tc_fence_before();

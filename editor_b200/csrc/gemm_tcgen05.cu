@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
     using S = GemmSmem<BN, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need a 1024-byte aligned base
+    uint8_t* smem = smem_raw;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
@@ -281,7 +281,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr int NCH = BN / 64;           // 32-column chunks per warp
         constexpr bool kAuxF32 = (EPI == EPI_RESIDUAL);
         constexpr bool kAuxBf16 = (EPI == EPI_GELU_BWD);
-        const uint32_t stg = smem_u32(smem + S::kStagingOffset + ew * 4096);
+        uint8_t* stg = smem + S::kStagingOffset + ew * 4096;
         const int lrow = lane >> 3;            // phase B: row within a group of 4
         const int lc4 = lane & 7;              // phase B: which float4 of the 32-column chunk
         int acc = 0;
@@ -353,7 +353,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                        make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
                 // ---- phase B
                 if (nvalid > 0) {
@@ -364,7 +365,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + lrow;
                         const int row = row_base + rr;
-                        const uint4 raw = lds128(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
+                        const uint4 raw = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
                         float4 v = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
                                                __uint_as_float(raw.w));
                         if (row >= M_rt) continue;
