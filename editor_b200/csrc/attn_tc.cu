@@ -287,20 +287,26 @@ int attention_tc_fwd(const EdbAttnDesc& d, cudaStream_t st) {
 // handled by two extra warps on CUDA cores.
 constexpr uint32_t BT_TILE = AT_KP * 128;                  // 18432
 constexpr uint32_t BT_SQ = 0, BT_SK = BT_TILE, BT_SV = 2 * BT_TILE, BT_SDO = 3 * BT_TILE, BT_SP = 4 * BT_TILE;
-constexpr uint32_t BT_BAR = 7 * BT_TILE;
-constexpr uint32_t BT_TOTAL = BT_BAR + 128 + 1024;
-constexpr uint32_t BT_TX = 2 * (128 * 128 + 128) + 2 * BT_TILE + 3 * (128 * 128 + 128);
-constexpr uint32_t BT_TM_DP = 0, BT_TM_DV = 192, BT_TM_DQ = 256, BT_TM_DK = 320;
+constexpr uint32_t BT_DSCOL = 6 * BT_TILE;                 // 144 floats: dS[:, key 128] per query line
+constexpr uint32_t BT_BAR = BT_DSCOL + 576;
+constexpr uint32_t BT_TOTAL = BT_BAR + 128;
+constexpr uint32_t BT_TX = 2 * (128 * 128 + 128) + 2 * BT_TILE + 2 * (128 * 128 + 128);
+// TMEM (256 columns, so that two CTAs share an SM): dP [0,128) is dead once dS is written; dQ and dK then reuse it
+constexpr uint32_t BT_TM_DP = 0, BT_TM_DV = 128, BT_TM_DQ = 0, BT_TM_DK = 64;
 
 struct AttnTcBwdParams {
     const __nv_bfloat16* qkv; long long ld_qkv;
     __nv_bfloat16* d_qkv;
+    const __nv_bfloat16* P;
     int H;
     float scale;
-    uint32_t idesc_dp, idesc_kk_mn, idesc_k_mn;   // (128x144 K/K), (128x64 MN/MN), (128x64 K/MN)
+    uint32_t idesc_dp, idesc_kk_mn, idesc_k_mn;   // (128x128 K/K), (128x64 MN/MN), (128x64 K/MN)
 };
 
-__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr) {
+// 64 accumulator columns of this thread's TMEM lane -> bf16 row in HBM, optionally plus a rank-1 term a * v[0..63] with v
+// a 128-byte row of a swizzled smem tile (the contribution of the key / query that is not on the MMA tile)
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr, float a = 0.f, const uint8_t* tile = nullptr,
+                                                 int line = 0) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
@@ -308,19 +314,52 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t ta
         tmem_ld_wait();
 #pragma unroll
         for (int t = 0; t < 32; t += 8) {
-            uint4 u;
-            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+            float v[8];
+#pragma unroll
+            for (int z = 0; z < 8; ++z) v[z] = __uint_as_float(r[t + z]);
+            if (tile != nullptr) {
+                const uint4 u = *reinterpret_cast<const uint4*>(tile + sw128(line, c * 4 + t / 8));
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    const float2 f = __bfloat1622float2(hh[z]);
+                    v[2 * z] = fmaf(a, f.x, v[2 * z]);
+                    v[2 * z + 1] = fmaf(a, f.y, v[2 * z + 1]);
+                }
+            }
+            uint4 o;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
             for (int z = 0; z < 4; ++z) {
-                __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[t + 2 * z]), __uint_as_float(r[t + 2 * z + 1]));
+                __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * z], v[2 * z + 1]);
                 w[z] = *reinterpret_cast<uint32_t*>(&hb);
             }
-            *reinterpret_cast<uint4*>(dst + c * 32 + t) = u;
+            *reinterpret_cast<uint4*>(dst + c * 32 + t) = o;
         }
     }
 }
 
-__global__ void __launch_bounds__(224, 1)
+// dot product of two 128-byte rows (64 bf16) of swizzled smem tiles
+__device__ __forceinline__ float dot_rows64(const uint8_t* ta, int la, const uint8_t* tb, int lb) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 ua = *reinterpret_cast<const uint4*>(ta + sw128(la, c));
+        const uint4 ub = *reinterpret_cast<const uint4*>(tb + sw128(lb, c));
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 fa = __bfloat1622float2(ha[t]), fb = __bfloat1622float2(hb[t]);
+            acc += fa.x * fb.x + fa.y * fb.y;
+        }
+    }
+    return acc;
+}
+
+// Query lines: 0..127 = tokens 1..128, 128 = token 0 (cls), 129..143 zero.  Keys 0..127 sit on the MMA tiles; key 128 is
+// handled on CUDA cores: its score column by the row-owner threads (one dot product each), its dK / dV row by warp 6.
+__global__ void __launch_bounds__(224, 2)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_constant__ CUtensorMap map_q1,
                    const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_do128,
                    const __grid_constant__ CUtensorMap map_do1, const __grid_constant__ CUtensorMap map_p128,
@@ -331,10 +370,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
     uint8_t* sK = smem + BT_SK;
     uint8_t* sV = smem + BT_SV;
     uint8_t* sdO = smem + BT_SDO;
-    uint8_t* sP = smem + BT_SP;            // 3 chunks of 64 keys; becomes dS
+    uint8_t* sP = smem + BT_SP;            // 2 chunks of 64 keys (keys 0..127); becomes dS
+    float* dscol = reinterpret_cast<float*>(smem + BT_DSCOL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BT_BAR);
-    uint64_t *bar_load = bars, *bar_dp = bars + 1, *bar_dv = bars + 2, *bar_pcol = bars + 3, *bar_ds = bars + 4,
-             *bar_dq = bars + 5, *bar_dk = bars + 6;
+    uint64_t *bar_load = bars, *bar_dp = bars + 1, *bar_dv = bars + 2, *bar_ds = bars + 4, *bar_dq = bars + 5,
+             *bar_dk = bars + 6;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -342,9 +382,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
     const int s = blk / p.H, h = blk % p.H;
     const int row0 = s * AT_L;
     const int HC = p.H * AT_HD;
+    const __nv_bfloat16* Pg = p.P + (size_t)blk * AT_L * AT_PLD;      // this (seq, head)'s [129][136] map
 
     // zero the 15 padding lines (129..143) of the query-indexed tiles
-    for (int t = threadIdx.x; t < 5 * 15 * 8; t += 224) {
+    for (int t = threadIdx.x; t < 4 * 15 * 8; t += 224) {
         const int tile = t / 120, rem = t % 120, line = 129 + rem / 8, c = rem % 8;
         uint8_t* base = tile == 0 ? sQ : (tile == 1 ? sdO : sP + (tile - 2) * BT_TILE);
         *reinterpret_cast<uint4*>(base + line * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -358,14 +399,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             mbar_init(bar_load, 1);
             mbar_init(bar_dp, 1);
             mbar_init(bar_dv, 1);
-            mbar_init(bar_pcol, 1);
             mbar_init(bar_ds, 128 + 1);
             mbar_init(bar_dq, 1);
             mbar_init(bar_dk, 1);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_ptr);
+        tmem_alloc<256>(tmem_ptr);
     }
     tc_fence_before();
     __syncthreads();
@@ -382,20 +422,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             tma_load_2d(sK, &map_kv, bar_load, HC + h * AT_HD, row0);
             tma_load_2d(sV, &map_kv, bar_load, 2 * HC + h * AT_HD, row0);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 tma_load_2d(sP + c * BT_TILE, &map_p128, bar_load, c * 64, blk * AT_L + 1);
                 tma_load_2d(sP + c * BT_TILE + 128 * 128, &map_p1, bar_load, c * 64, blk * AT_L);
             }
             mbar_wait(bar_load, 0);
             tc_fence_after();
             const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), av = smem_u32(sV), ado = smem_u32(sdO), ap = smem_u32(sP);
-            // dP = dO V^T
+            // dP[q 0..127][key 0..127] = dO V^T
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 tc_mma_bf16(tmem + BT_TM_DP, make_smem_desc(ado + k * 32, 0, 1024), make_smem_desc(av + k * 32, 0, 1024),
                             p.idesc_dp, k > 0);
             tc_commit(bar_dp);
-            // dV = P^T dO   (A: P MN-major over keys 0..127, reduction over the 144 query lines)
+            // dV[key 0..127] = P^T dO   (A: P MN-major, reduction over the 144 query lines)
 #pragma unroll
             for (int k = 0; k < AT_KP / 16; ++k)
                 tc_mma_bf16(tmem + BT_TM_DV, make_smem_desc(ap + k * 2048, BT_TILE, 1024),
@@ -403,13 +443,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             tc_commit(bar_dv);
             mbar_wait(bar_ds, 0);
             tc_fence_after();
-            // dQ = dS K     (A: dS K-major, 3 chunks of 64 keys;  B: K MN-major)
+            // dQ[q 0..127] = dS K over keys 0..127   (key 128 is added by the epilogue threads)
 #pragma unroll
-            for (int k = 0; k < AT_KP / 16; ++k)
+            for (int k = 0; k < 8; ++k)
                 tc_mma_bf16(tmem + BT_TM_DQ, make_smem_desc(ap + (k >> 2) * BT_TILE + (k & 3) * 32, 0, 1024),
                             make_smem_desc(ak + k * 2048, BT_TILE, 1024), p.idesc_k_mn, k > 0);
             tc_commit(bar_dq);
-            // dK = dS^T Q   (A: dS MN-major over keys 0..127;  B: Q MN-major, reduction over the 144 query lines)
+            // dK[key 0..127] = dS^T Q   (reduction over the 144 query lines)
 #pragma unroll
             for (int k = 0; k < AT_KP / 16; ++k)
                 tc_mma_bf16(tmem + BT_TM_DK, make_smem_desc(ap + k * 2048, BT_TILE, 1024),
@@ -418,6 +458,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         }
     } else if (warp == 5) {
         // ---------------- cls query (token 0 = query line 128) on CUDA cores
+        const float p0_128 = __bfloat162float(Pg[128]);
         mbar_wait(bar_load, 0);
         float g[AT_HD];
 #pragma unroll
@@ -430,13 +471,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                 g[c * 8 + 2 * t] = f.x; g[c * 8 + 2 * t + 1] = f.y;
             }
         }
-        float ds[5];
+        float ds[5], pv[5];
         float dsum = 0.f;
 #pragma unroll
         for (int jj = 0; jj < 5; ++jj) {
             const int j = jj * 32 + lane;
-            float acc = 0.f, pv = 0.f;
-            if (j < AT_KP) {
+            float acc = 0.f;
+            pv[jj] = 0.f;
+            if (j < AT_L) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint4 u = *reinterpret_cast<const uint4*>(sV + sw128(j, c));
@@ -447,28 +489,23 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
                         acc += g[c * 8 + 2 * t] * f.x + g[c * 8 + 2 * t + 1] * f.y;
                     }
                 }
-                pv = lds_bf16(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2);
-                if (pv == 0.f) acc = 0.f;       // padded keys: garbage V rows must not leak through 0 * inf
+                pv[jj] = j < 128 ? lds_bf16(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2) : p0_128;
             }
             ds[jj] = acc;                        // dP_0j for now
-            dsum += acc * pv;
+            dsum += acc * pv[jj];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-        mbar_wait(bar_dv, 0);                    // P is no longer read by the dV MMA
-        mbar_wait(bar_pcol, 0);                  // ... nor by the key-128 warp
+        mbar_wait(bar_dv, 0);                    // line 128 of P is no longer read by the dV MMA: overwrite it with dS
 #pragma unroll
         for (int jj = 0; jj < 5; ++jj) {
             const int j = jj * 32 + lane;
-            if (j < AT_KP) {
-                __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2);
-                const float pv = __bfloat162float(*pa);
-                const __nv_bfloat16 d16 = __float2bfloat16(pv * (ds[jj] - dsum) * p.scale);
-                *pa = d16;
-                ds[jj] = __bfloat162float(d16);
-            } else {
-                ds[jj] = 0.f;
-            }
+            const __nv_bfloat16 d16 = __float2bfloat16(pv[jj] * (ds[jj] - dsum) * p.scale);
+            ds[jj] = j < AT_L ? __bfloat162float(d16) : 0.f;
+            if (j < 128)
+                *reinterpret_cast<__nv_bfloat16*>(sP + (j >> 6) * BT_TILE + sw128(128, (j & 63) >> 3) + (j & 7) * 2) = d16;
+            else if (j == 128)
+                dscol[128] = ds[jj];
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -488,16 +525,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         *reinterpret_cast<__nv_bfloat162*>(p.d_qkv + (size_t)row0 * p.ld_qkv + h * AT_HD + 2 * lane) =
             __floats2bfloat162_rn(o0, o1);
     } else if (warp == 6) {
-        // ---------------- key 128 (the 129th key) on CUDA cores: dV[128] = sum_i P[i][128] dO[i], dK[128] = sum_i dS[i][128] Q[i]
-        mbar_wait(bar_load, 0);
+        // ---------------- key 128 on CUDA cores: dV[128] = sum_i P[i][128] dO[i],  dK[128] = sum_i dS[i][128] Q[i]
         float col[5];
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
-            const int i = ii * 32 + lane;        // query line
-            col[ii] = i < AT_L ? lds_bf16(sP + 2 * BT_TILE + sw128(i, 0)) : 0.f;
+            const int i = ii * 32 + lane;        // query line i <-> token (i < 128 ? i + 1 : 0)
+            col[ii] = i < AT_L ? __bfloat162float(Pg[(size_t)(i < 128 ? i + 1 : 0) * AT_PLD + 128]) : 0.f;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_pcol);
+        mbar_wait(bar_load, 0);
         float o0 = 0.f, o1 = 0.f;
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
@@ -516,7 +551,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int i = ii * 32 + lane;
-            col[ii] = i < AT_L ? lds_bf16(sP + 2 * BT_TILE + sw128(i, 0)) : 0.f;
+            col[ii] = i < AT_L ? dscol[i] : 0.f;
         }
         o0 = o1 = 0.f;
 #pragma unroll
@@ -535,68 +570,65 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         // ---------------- thread i: query line i (token i+1) for dS / dQ, key i (token i) for dK / dV
         const int i = threadIdx.x;
         const uint32_t tB = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const float p128 = __bfloat162float(Pg[(size_t)(i + 1) * AT_PLD + 128]);     // P[token i+1][key 128]
         mbar_wait(bar_load, 0);
+        const float dp128 = dot_rows64(sdO, i, sV, 128);                              // dP[i][128] = dO_i . V_128
         mbar_wait(bar_dp, 0);
         tc_fence_after();
-        float delta = 0.f;
+        float delta = p128 * dp128;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {            // 32 score columns per pass (the last pass: 16)
+        for (int c = 0; c < 4; ++c) {            // 32 score columns per pass
             uint32_t r[32];
-            if (c < 4) tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
-            else tmem_ld_32x16(tB + BT_TM_DP + 128, *reinterpret_cast<uint32_t(*)[16]>(r));
+            tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
             tmem_ld_wait();
-            const int nq = c < 4 ? 4 : 2;
 #pragma unroll
-            for (int q = 0; q < nq; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
                 const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float2 f = __bfloat1622float2(hh[t]);
-                    if (f.x != 0.f) delta += f.x * __uint_as_float(r[q * 8 + 2 * t]);
-                    if (f.y != 0.f) delta += f.y * __uint_as_float(r[q * 8 + 2 * t + 1]);
+                    delta += f.x * __uint_as_float(r[q * 8 + 2 * t]) + f.y * __uint_as_float(r[q * 8 + 2 * t + 1]);
                 }
             }
         }
-        mbar_wait(bar_dv, 0);
-        mbar_wait(bar_pcol, 0);
+        const float ds128 = __bfloat162float(__float2bfloat16(p128 * (dp128 - delta) * p.scale));
+        dscol[i] = ds128;
+        mbar_wait(bar_dv, 0);                    // P is no longer read by the dV MMA: overwrite it with dS
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
+        for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
-            if (c < 4) tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
-            else tmem_ld_32x16(tB + BT_TM_DP + 128, *reinterpret_cast<uint32_t(*)[16]>(r));
+            tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
             tmem_ld_wait();
-            const int nq = c < 4 ? 4 : 2;
 #pragma unroll
-            for (int q = 0; q < nq; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 uint4* pa = reinterpret_cast<uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
                 uint4 u = *pa;
                 __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float2 f = __bfloat1622float2(hh[t]);
-                    const float a = f.x != 0.f ? f.x * (__uint_as_float(r[q * 8 + 2 * t]) - delta) * p.scale : 0.f;
-                    const float b = f.y != 0.f ? f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale : 0.f;
-                    hh[t] = __floats2bfloat162_rn(a, b);
+                    hh[t] = __floats2bfloat162_rn(f.x * (__uint_as_float(r[q * 8 + 2 * t]) - delta) * p.scale,
+                                                  f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale);
                 }
                 *pa = u;
             }
         }
+        tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(bar_ds);
-        tc_fence_after();
         __nv_bfloat16* krow = p.d_qkv + (size_t)(row0 + i) * p.ld_qkv + h * AT_HD;
-        store_row64_bf16(krow + 2 * HC, tB + BT_TM_DV);                       // dV[key i]
+        store_row64_bf16(krow + 2 * HC, tB + BT_TM_DV);                                           // dV[key i]
         mbar_wait(bar_dq, 0);
         tc_fence_after();
-        store_row64_bf16(p.d_qkv + (size_t)(row0 + 1 + i) * p.ld_qkv + h * AT_HD, tB + BT_TM_DQ);   // dQ[token i+1]
+        store_row64_bf16(p.d_qkv + (size_t)(row0 + 1 + i) * p.ld_qkv + h * AT_HD, tB + BT_TM_DQ, ds128, sK, 128);   // dQ[token i+1]
         mbar_wait(bar_dk, 0);
         tc_fence_after();
-        store_row64_bf16(krow + HC, tB + BT_TM_DK);                           // dK[key i]
+        store_row64_bf16(krow + HC, tB + BT_TM_DK);                                               // dK[key i]
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<512>(tmem);
+    if (warp == 4) tmem_dealloc<256>(tmem);
 }
 
 int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st) {
@@ -613,8 +645,9 @@ int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st) {
     EDB_TRY(make_tmap_bf16(&mp1, d.P, AT_PLD, (long long)d.nseq * d.heads * AT_L, AT_PLD, 1));
     AttnTcBwdParams p{};
     p.qkv = (const __nv_bfloat16*)d.qkv; p.ld_qkv = d.ld_qkv; p.d_qkv = (__nv_bfloat16*)d.d_qkv;
+    p.P = (const __nv_bfloat16*)d.P;
     p.H = d.heads; p.scale = d.scale;
-    p.idesc_dp = make_idesc_bf16(128, AT_KP, 0, 0);
+    p.idesc_dp = make_idesc_bf16(128, 128, 0, 0);
     p.idesc_kk_mn = make_idesc_bf16(128, AT_HD, 1, 1);
     p.idesc_k_mn = make_idesc_bf16(128, AT_HD, 0, 1);
     static bool configured = false;
