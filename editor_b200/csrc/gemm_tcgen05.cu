@@ -361,7 +361,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const bool vD = vec && (p.ldd % 4 == 0), v2 = vec && (p.ld_out2 % 4 == 0);
                     // static register indexing of the prefetched aux operand needs the full unroll; the other
                     // epilogues keep the loop rolled up (instruction-cache footprint)
-#pragma unroll(kAuxF32 || kAuxBf16 ? 8 : 2)
+#pragma unroll(kAuxF32 || kAuxBf16 ? 8 : 4)
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + lrow;
                         const int row = row_base + rr;

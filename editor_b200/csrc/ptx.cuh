@@ -37,14 +37,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the hint
+    // expires) instead of burning issue slots of its scheduler, which the epilogue warps on the same sub-partition need
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 
