@@ -3,7 +3,8 @@
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier full/empty)
 //   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma, 128 x BN x 16 per instruction, fp32 in TMEM)
 //   warp 2      : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 4..11 : epilogue      (tcgen05.ld -> bias / GELU / residual / GELU' / split-K reduce -> global)
+//   warps 4..   : epilogue      (8 or 16 warps: tcgen05.ld -> smem transpose -> bias / GELU / residual / GELU' / split-K
+//                                reduce -> coalesced global; 16 warps for the arithmetic-heavy and store-heavy variants)
 //
 // Both operands may be K-major (reduction dim contiguous) or MN-major (reduction dim strided); that covers the
 // forward (X W^T), dgrad (dY W) and wgrad (dY^T X) products of every Linear on EDITOR's hot path
@@ -11,13 +12,18 @@
 #include "ptx.cuh"
 #include "abi_internal.h"
 
+#ifndef EDB_GELU_EPI_WARPS
+#define EDB_GELU_EPI_WARPS 16
+#endif
+
 namespace edb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumEpiWarps = 8;
-constexpr int kThreads = 128 + kNumEpiWarps * 32;
+// epilogue warps per CTA: 8 (32-column chunks) or 16 (16-column chunks; twice the warps per scheduler to hide the FMA /
+// shared-memory latencies of the arithmetic-heavy GELU epilogues)
+template <int NEPI> constexpr int gemm_threads() { return 128 + NEPI * 32; }
 
 struct GemmKernelParams {
     int M, N, K;
@@ -91,7 +97,7 @@ struct GemmSmem {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStagingOffset = STAGES * kStageBytes;           // 8 epilogue warps x 4 KB transpose patches
-    static constexpr int kBarOffset = kStagingOffset + kNumEpiWarps * 4096;
+    static constexpr int kBarOffset = kStagingOffset + 8 * 4096;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // + alignment slack
 };
 
@@ -141,8 +147,8 @@ __device__ __forceinline__ void st4g(__nv_bfloat16* p, const float4& v, int nval
     if (nvalid > 3) p[3] = __float2bfloat16(v.w);
 }
 
-template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int STAGES, int EPI, int NEPI>
+__global__ void __launch_bounds__(gemm_threads<NEPI>(), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
     using S = GemmSmem<BN, STAGES>;
@@ -168,7 +174,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kNumEpiWarps);
+            mbar_init(&tmem_empty[i], NEPI);
         }
         fence_barrier_init();
     }
@@ -277,31 +283,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // c+1 (residual stream / saved pre-activation) is fetched while chunk c is processed.
         const int ew = warp - 4;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may read
-        const int half = ew >> 2;              // column half
-        constexpr int NCH = BN / 64;           // 32-column chunks per warp
+        const int part = ew >> 2;              // column part (NEPI/4 parts per tile)
+        constexpr int NPART = NEPI / 4;
+        constexpr int CW = 256 / NEPI;         // chunk width in columns: 32 (8 warps) or 16 (16 warps)
+        constexpr int NCH = BN / NPART / CW;   // chunks per warp
+        constexpr int LPR = CW / 4;            // phase B: lanes per row (each lane 4 columns)
+        constexpr int RPA = 32 / LPR;          // phase B: rows per access
+        constexpr int NIT = 32 / RPA;          // phase B: accesses per chunk
+        constexpr int RB = CW * 4;             // bytes per patch row
         constexpr bool kAuxF32 = (EPI == EPI_RESIDUAL);
         constexpr bool kAuxBf16 = (EPI == EPI_GELU_BWD);
-        uint8_t* stg = smem + S::kStagingOffset + ew * 4096;
-        const int lrow = lane >> 3;            // phase B: row within a group of 4
-        const int lc4 = lane & 7;              // phase B: which float4 of the 32-column chunk
+        uint8_t* stg = smem + S::kStagingOffset + ew * (32 * RB);
+        const int lrow = lane / LPR;           // phase B: row within a group of RPA
+        const int lc4 = lane % LPR;            // phase B: which float4 of the chunk
+        // conflict-free 16-byte slot of (row, logical slot) inside the patch
+        auto slot = [](int row, int j) { return CW == 32 ? (j ^ (row & 7)) : (j ^ ((row >> 1) & 3)); };
         int acc = 0;
         uint32_t acc_phase = 0;
-        float4 axf_c[kAuxF32 ? 8 : 1], axf_n[kAuxF32 ? 8 : 1];     // fp32 aux: current / next chunk
-        uint2 axh_c[kAuxBf16 ? 8 : 1], axh_n[kAuxBf16 ? 8 : 1];     // bf16 aux
+        float4 axf_c[kAuxF32 ? NIT : 1], axf_n[kAuxF32 ? NIT : 1];     // fp32 aux: current / next chunk
+        uint2 axh_c[kAuxBf16 ? NIT : 1], axh_n[kAuxBf16 ? NIT : 1];     // bf16 aux
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             int tm, tn, ks;
             decode(w, tm, tn, ks);
             if (ks * kb_per_split >= kb_total) continue;      // empty split: the issuer skipped it too
             const int row_base = tm * BM + quarter * 32;
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            const int colw = tn * BN + half * (BN / 2) + lc4 * 4;
+            const int colw = tn * BN + part * (BN / NPART) + lc4 * 4;
             auto load_aux = [&](int c) {
-                const int col = colw + c * 32;
+                const int col = colw + c * CW;
                 const int nvalid = p.N - col;
                 if (kAuxF32) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = row_base + it * 4 + lrow;
+                    for (int it = 0; it < NIT; ++it) {
+                        const int row = row_base + it * RPA + lrow;
                         axf_n[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (row < M_rt && nvalid > 0)
                             axf_n[it] = ld4g(reinterpret_cast<const float*>(p.aux) + (size_t)row * p.ld_aux + col, nvalid,
@@ -310,8 +324,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 if (kAuxBf16) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = row_base + it * 4 + lrow;
+                    for (int it = 0; it < NIT; ++it) {
+                        const int row = row_base + it * RPA + lrow;
                         axh_n[it] = make_uint2(0u, 0u);
                         if (row < M_rt && nvalid > 0) {
                             const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)row * p.ld_aux + col;
@@ -332,28 +346,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-                const int col_t = half * (BN / 2) + c * 32;
-                const int col = colw + c * 32;                      // first of this lane's 4 columns in phase B
+                const int col_t = part * (BN / NPART) + c * CW;
+                const int col = colw + c * CW;                      // first of this lane's 4 columns in phase B
                 const int nvalid = p.N - col;                        // >= 4: all four columns exist
                 const bool vec = nvalid >= 4;
                 if (kAuxF32) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) axf_c[it] = axf_n[it];
+                    for (int it = 0; it < NIT; ++it) axf_c[it] = axf_n[it];
                 }
                 if (kAuxBf16) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) axh_c[it] = axh_n[it];
+                    for (int it = 0; it < NIT; ++it) axh_c[it] = axh_n[it];
                 }
                 // ---- phase A
-                uint32_t r[32];
-                tmem_ld_32x32(t_base + col_t, r);
+                uint32_t r[CW];
+                if constexpr (CW == 32) tmem_ld_32x32(t_base + col_t, r);
+                else tmem_ld_32x16(t_base + col_t, r);
                 if (c + 1 < NCH) load_aux(c + 1);
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias != nullptr && EPI != EPI_ATOMIC && nvalid > 0) b4 = ld4g(p.bias + col, nvalid, vec);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                for (int j = 0; j < LPR; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * RB + (slot(lane, j) << 4)) =
                         make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
                 // ---- phase B
@@ -361,11 +376,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const bool vD = vec && (p.ldd % 4 == 0), v2 = vec && (p.ld_out2 % 4 == 0);
                     // static register indexing of the prefetched aux operand needs the full unroll; the other
                     // epilogues keep the loop rolled up (instruction-cache footprint)
-#pragma unroll(kAuxF32 || kAuxBf16 ? 8 : 4)
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = it * 4 + lrow;
+#pragma unroll(kAuxF32 || kAuxBf16 ? NIT : 4)
+                    for (int it = 0; it < NIT; ++it) {
+                        const int rr = it * RPA + lrow;
                         const int row = row_base + rr;
-                        const uint4 raw = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((lc4 ^ (rr & 7)) << 4));
+                        const uint4 raw = *reinterpret_cast<const uint4*>(stg + rr * RB + (slot(rr, lc4) << 4));
                         float4 v = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
                                                __uint_as_float(raw.w));
                         if (row >= M_rt) continue;
@@ -464,19 +479,19 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int NEPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, cudaStream_t stream) {
     using S = GemmSmem<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, NEPI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
         configured = true;
     }
     const int num_work = p.m_tiles * p.n_tiles * p.split_k;
     const int grid = num_work < num_sms() ? num_work : num_sms();
-    gemm_bf16_kernel<BN, STAGES, EPI><<<grid, kThreads, S::kTotal, stream>>>(ta, tb, p);
+    gemm_bf16_kernel<BN, STAGES, EPI, NEPI><<<grid, gemm_threads<NEPI>(), S::kTotal, stream>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
     return EDB_OK;
@@ -518,16 +533,16 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     if (!g.b_mn_major) rc = make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN);
     else               rc = make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BK);
     if (rc != EDB_OK) return rc;
-#define EDB_LAUNCH_EPI(E)                                             \
-    case E:                                                           \
-        if (BN == 256) return launch_gemm<256, 4, E>(ta, tb, p, stream); \
-        return launch_gemm<128, 6, E>(ta, tb, p, stream);
+#define EDB_LAUNCH_EPI(E, W)                                             \
+    case E:                                                              \
+        if (BN == 256) return launch_gemm<256, 4, E, W>(ta, tb, p, stream); \
+        return launch_gemm<128, 6, E, W>(ta, tb, p, stream);
     switch (g.epilogue) {
-        EDB_LAUNCH_EPI(EPI_STORE)
-        EDB_LAUNCH_EPI(EPI_GELU)
-        EDB_LAUNCH_EPI(EPI_RESIDUAL)
-        EDB_LAUNCH_EPI(EPI_GELU_BWD)
-        EDB_LAUNCH_EPI(EPI_ATOMIC)
+        EDB_LAUNCH_EPI(EPI_STORE, 16)
+        EDB_LAUNCH_EPI(EPI_GELU, EDB_GELU_EPI_WARPS)
+        EDB_LAUNCH_EPI(EPI_RESIDUAL, 8)
+        EDB_LAUNCH_EPI(EPI_GELU_BWD, EDB_GELU_EPI_WARPS)
+        EDB_LAUNCH_EPI(EPI_ATOMIC, 8)
         default:
             return edb_set_error(EDB_ERR_UNSUPPORTED, "gemm: unknown epilogue");
     }
