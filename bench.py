@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--impl", default="own")
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-mode", type=int, default=0, help="0 = CTA-pair tcgen05 tiles (default), 1 = single-CTA tiles")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -179,6 +180,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from editor_b200 import lib
     from editor_b200.train import Trainer
+    lib.gemm_set_mode(args.gemm_mode)
     B = args.batch
     model, sd, x, label, cam = build_case(device, B, seed=1 + rank)
     model.train()
@@ -237,8 +239,16 @@ def main():
     tm = lib.gemm_timing
     lib.gemm_timing = None
     if rank == 0:
-        fl = sum(f for f, _, _ in tm)
-        tt = sum(a.elapsed_time(b) for _, a, b in tm) * 1e-3
+        fl = sum(f for f, _, _, _ in tm)
+        tt = sum(a.elapsed_time(b) for _, a, b, _ in tm) * 1e-3
+        shapes = {}
+        for f, a, b, key in tm:
+            r = shapes.setdefault(key, [0, 0.0, 0.0])
+            r[0] += 1
+            r[1] += a.elapsed_time(b)
+            r[2] += f
+        gemm_table = [{"shape": k, "launches": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / v[1] / 1e9, 1)}
+                      for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -254,6 +264,8 @@ def main():
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch_mean": None,
                 "launches_per_step": len(tm), "gemm_ms_per_step": tt * 1e3,
+                "tile": "CTA pair 256x256 (cta_group::2)" if args.gemm_mode == 0 else "single CTA 128x256",
+                "by_shape": gemm_table[:16],
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)"}
     eng = model.engine()
     eng.stats["events"] = []

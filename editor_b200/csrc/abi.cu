@@ -21,6 +21,8 @@ int edb_gemm_bf16(const EdbGemmDesc* d, void* stream) {
     return edb::gemm_bf16(*d, static_cast<cudaStream_t>(stream));
 }
 
+int edb_gemm_set_mode(int mode) { return edb::gemm_set_mode(mode); }
+
 #define ST static_cast<cudaStream_t>(stream)
 
 int edb_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,

@@ -25,6 +25,7 @@ int edb_set_error(int code, const char* msg);
 int num_sms();
 int make_tmap_bf16(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_rows);
 int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream);
+int gemm_set_mode(int mode);
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, void* y,
                   long long ldy, int y_f32, float* mean, float* rstd, int rows, int dim, const int* rows_dev,

@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libeditor_b200.so")
+# EDB_LIB selects another build of the same library (e.g. the -DEDB_MBAR_TIMEOUT debug copy, csrc/Makefile)
+LIB_PATH = os.environ.get("EDB_LIB") or os.path.join(_HERE, "lib", "libeditor_b200.so")
 
 EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_GELU_BWD, EPI_ATOMIC = 0, 1, 2, 3, 4
 PREC_BF16, PREC_FP32 = 0, 1
@@ -57,6 +58,7 @@ SIGNATURES = {
     "edb_version": (c_int, []),
     "edb_last_error": (ctypes.c_char_p, []),
     "edb_gemm_bf16": (c_int, [ctypes.POINTER(GemmDesc), c_vp]),
+    "edb_gemm_set_mode": (c_int, [c_int]),
     "edb_layernorm_fwd": (c_int, [c_vp, c_ll, c_vp, c_vp, c_float, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_int, c_vp,
                                   c_vp]),
     "edb_cast_rows_f32_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
@@ -112,6 +114,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("EDB_GEMM_MODE"):           # A/B runs: 1 = single-CTA GEMM tiles (see edb_gemm_set_mode)
+            lib.edb_gemm_set_mode(int(os.environ["EDB_GEMM_MODE"]))
         _lib = lib
     return _lib
 
@@ -143,6 +147,11 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
 
 
+def gemm_set_mode(mode):
+    """0 = automatic (CTA pairs, tcgen05.mma.cta_group::2), 1 = single-CTA tiles only."""
+    check(load().edb_gemm_set_mode(mode))
+
+
 def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None, aux=None, out2=None,
          alpha=1.0, split_k=1, row_scale=None, scale_group=1, M_dev=None, K_dev=None):
     """D[M,N] = epi(sum_k A(m,k) B(n,k)); A/B bf16 CUDA tensors, D bf16 or fp32 (2-D, row pitch = stride(0))."""
@@ -167,7 +176,8 @@ def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None
         e0.record()
         call("edb_gemm_bf16", ctypes.byref(d), stream_ptr())
         e1.record()
-        gemm_timing.append((2.0 * M * N * K, e0, e1))
+        gemm_timing.append((2.0 * M * N * K, e0, e1, "%dx%dx%d %s%s epi%d%s" % (
+            M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", epilogue, " sk%d" % split_k if split_k > 1 else "")))
         return D
     call("edb_gemm_bf16", ctypes.byref(d), stream_ptr())
     return D

@@ -67,6 +67,10 @@ typedef struct EdbGemmDesc {
 } EdbGemmDesc;
 
 int edb_gemm_bf16(const EdbGemmDesc* desc, void* stream);
+/* Tile mode of edb_gemm_bf16 (process-wide): 0 = automatic -- CTA pairs running tcgen05.mma.cta_group::2 (256 x 256 x 16)
+ * wherever N > 128 and M > 128 --, 1 = single-CTA 128 x 256 tiles only.  Results are bit-identical in both modes (same
+ * accumulation order); the switch exists for A/B timing and for the tests that prove exactly that. */
+int edb_gemm_set_mode(int mode);
 
 /* ---- row kernels (HBM-bound) ------------------------------------------------------------------------------ */
 

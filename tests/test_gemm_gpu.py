@@ -83,22 +83,91 @@ def test_gemm_gelu_bwd_and_splitk():
     assert (dW - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (129 * 6, 768, 768), (1000, 2304, 200), (49536 // 8, 3072, 768)])
+def test_gemm_cta_pair_equals_single_cta(M, N, K, a_mn, b_mn):
+    """The cta_group::2 path (256 x 256 MMA over a CTA pair) accumulates in the same order as the single-CTA path:
+    bit-identical results, including the ragged last pair tile (M not a multiple of 256) and a device-side row count."""
+    from editor_b200 import lib
+    Kp, Mp, Np = (K + 7) // 8 * 8, (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = _mk(K, Mp, 21)[:, :M] if a_mn else _mk(M, Kp, 21)[:, :K]
+    B = _mk(K, Np, 22)[:, :N] if b_mn else _mk(N, Kp, 22)[:, :K]
+    bias = torch.randn(N, device="cuda")
+    m_dev = torch.tensor([M - 131], dtype=torch.int32, device="cuda")
+    outs = []
+    try:
+        for mode in (1, 0):
+            lib.gemm_set_mode(mode)
+            D = torch.full((M, N), 7.0, dtype=torch.float32, device="cuda")
+            D2 = torch.full((M, N), 7.0, dtype=torch.float32, device="cuda")
+            lib.gemm(A, B, D, M, N, K, a_mn=a_mn, b_mn=b_mn, bias=bias)
+            lib.gemm(A, B, D2, M, N, K, a_mn=a_mn, b_mn=b_mn, M_dev=m_dev.data_ptr())
+            torch.cuda.synchronize()
+            outs.append((D, D2))
+    finally:
+        lib.gemm_set_mode(0)
+    ref = _ref(A, B, a_mn, b_mn) + bias
+    assert (outs[1][0] - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.all(outs[1][1][M - 131:] == 7.0)      # rows beyond the device-side count stay untouched
+
+
+def test_gemm_cta_pair_epilogues_and_splitk_equal_single_cta():
+    from editor_b200 import lib
+    M, N, K = 129 * 10, 3072, 768
+    A, W1, W2 = _mk(M, K, 31, 0.5), _mk(N, K, 32, 0.05), _mk(K, N, 33, 0.05)
+    H = _mk(M, N, 34, 0.5)
+    bias, bias2 = torch.randn(N, device="cuda") * 0.1, torch.randn(K, device="cuda") * 0.1
+    res = torch.randn(M, K, device="cuda")
+    scale = torch.rand(10, device="cuda")
+    outs = []
+    try:
+        for mode in (1, 0):
+            lib.gemm_set_mode(mode)
+            g, pre = (torch.empty(M, N, dtype=torch.bfloat16, device="cuda") for _ in range(2))
+            lib.gemm(A, W1, g, M, N, K, epilogue=lib.EPI_GELU, bias=bias, out2=pre)
+            r = torch.empty(M, K, device="cuda")
+            lib.gemm(H, W2, r, M, K, N, epilogue=lib.EPI_RESIDUAL, bias=bias2, aux=res, row_scale=scale, scale_group=129)
+            db = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+            lib.gemm(A, W2, db, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=H)
+            dW = torch.zeros(N, K, device="cuda")
+            lib.gemm(H, A, dW, N, K, M, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=1)
+            dW4 = torch.zeros(N, K, device="cuda")
+            lib.gemm(H, A, dW4, N, K, M, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=4)
+            torch.cuda.synchronize()
+            outs.append((g, pre, r, db, dW, dW4))
+    finally:
+        lib.gemm_set_mode(0)
+    for a, b in list(zip(*outs))[:5]:
+        assert torch.equal(a, b)
+    ref = H.float().t() @ A.float()
+    assert (outs[1][5] - ref).abs().max().item() < 2e-3 * ref.abs().max().item()   # split-K: atomic order is free
+    ref_r = res + scale.repeat_interleave(129)[:, None] * (H.float() @ W2.float().t() + bias2)
+    assert (outs[1][2] - ref_r).abs().max().item() < 2e-3 * ref_r.abs().max().item()
+
+
 def test_gemm_throughput_report(capsys):
     """Not an assertion on speed: prints TFLOP/s of the fc1-shaped GEMM for the log."""
     from editor_b200 import lib
     M, N, K = 49536, 3072, 768
     A, B = _mk(M, K, 12, 0.5), _mk(N, K, 13, 0.05)
     D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    for _ in range(3):
-        lib.gemm(A, B, D, M, N, K)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(10):
-        lib.gemm(A, B, D, M, N, K)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / 10
-    with capsys.disabled():
-        print("\n[gemm 49536x3072x768 bf16] %.3f ms  %.1f TFLOP/s" % (ms, 2.0 * M * N * K / ms / 1e9))
+    try:
+        for mode, name in ((1, "single CTA 128x256"), (0, "CTA pair 256x256")):
+            lib.gemm_set_mode(mode)
+            for _ in range(3):
+                lib.gemm(A, B, D, M, N, K)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                lib.gemm(A, B, D, M, N, K)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / 10
+            with capsys.disabled():
+                print("\n[gemm 49536x3072x768 bf16, %s] %.3f ms  %.1f TFLOP/s" % (name, ms, 2.0 * M * N * K / ms / 1e9))
+    finally:
+        lib.gemm_set_mode(0)
     ref = A[:256].float() @ B.float().t()
     assert (D[:256].float() - ref).abs().max().item() < 5e-2

@@ -40,8 +40,13 @@ def main():
     g3072 = torch.zeros(3072, 768, device=dev); g768x = torch.zeros(768, 3072, device=dev)
     rows = []
     def add(name, flops, fn):
-        ms = t(fn)
-        rows.append((name, ms, flops / ms / 1e9))
+        res = []
+        for mode in (1, 0):          # 1 = single-CTA 128x256 tiles, 0 = CTA pairs (cta_group::2, 256x256)
+            lib.gemm_set_mode(mode)
+            ms = t(fn)
+            res += [ms, flops / ms / 1e9]
+        lib.gemm_set_mode(0)
+        rows.append((name, *res))
     add("qkv fwd  [M,768]x[2304,768] bias bf16", 2*M*2304*768, lambda: lib.gemm(x768, w_qkv, o2304, M, 2304, 768, bias=b2304))
     add("proj fwd [M,768]x[768,768] residual f32", 2*M*768*768, lambda: lib.gemm(x768, w_proj, res2, M, 768, 768, epilogue=lib.EPI_RESIDUAL, bias=b768, aux=res))
     add("fc1 fwd  [M,768]x[3072,768] gelu + pre", 2*M*3072*768, lambda: lib.gemm(x768, w_fc1, o3072, M, 3072, 768, epilogue=lib.EPI_GELU, bias=b3072, out2=o3072b))
@@ -54,11 +59,13 @@ def main():
     add("fc1 wgrad [3072,768] splitK2", 2*M*3072*768, lambda: lib.gemm(x3072, x768, g3072, 3072, 768, M, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=2))
     add("proj wgrad [768,768] splitK8", 2*M*768*768, lambda: lib.gemm(x768, x768, g768, 768, 768, M, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=8))
     add("qkv wgrad [2304,768] splitK8", 2*M*2304*768, lambda: lib.gemm(x2304, x768, g2304, 2304, 768, M, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC, split_k=8))
-    tot = 0
-    for name, ms, tf in rows:
-        print("%-44s %7.3f ms %7.1f TFLOP/s" % (name, ms, tf))
-        tot += ms
-    print("sum per layer: %.3f ms" % tot)
+    tot1 = tot2 = 0
+    print("%-44s %22s   %22s" % ("", "single CTA 128x256", "CTA pair 256x256"))
+    for name, ms1, tf1, ms2, tf2 in rows:
+        print("%-44s %7.3f ms %7.1f TF/s   %7.3f ms %7.1f TF/s" % (name, ms1, tf1, ms2, tf2))
+        tot1 += ms1
+        tot2 += ms2
+    print("sum per layer: %.3f ms (single)  %.3f ms (pair)" % (tot1, tot2))
 
 
 if __name__ == "__main__":
