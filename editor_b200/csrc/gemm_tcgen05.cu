@@ -344,6 +344,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t acc_phase = 0;
         float4 axf_c[kAuxF32 ? NIT : 1], axf_n[kAuxF32 ? NIT : 1];     // fp32 aux: current / next chunk
         uint2 axh_c[kAuxBf16 ? NIT : 1], axh_n[kAuxBf16 ? NIT : 1];     // bf16 aux
+        float rsc[kAuxF32 ? NIT : 1];                                   // DropPath row scales of this lane's rows
+        // INTERIOR tiles (all 32 rows and all columns of the warp's slab in range, 16-byte aligned pitches -- every tile
+        // of the backbone GEMMs except the last row tile) take a path without per-element predicates and with
+        // incremental row pointers; the generic path below handles ragged edges, odd pitches and the fp32 GELU.
+        const bool pitch_ok = (p.ldd % 4 == 0) && (p.out2 == nullptr || p.ld_out2 % 4 == 0) &&
+                              (p.aux == nullptr || p.ld_aux % 4 == 0) && !(EPI == EPI_GELU && p.out_f32);
+        const size_t d_step = (size_t)RPA * p.ldd, o2_step = (size_t)RPA * p.ld_out2, aux_step = (size_t)RPA * p.ld_aux;
         for (int w = unit; w < num_work; w += units) {
             int tm, tn, ks;
             decode(w, tm, tn, ks);
@@ -351,8 +358,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int row_base = (tm * CG + (int)rank) * BM + quarter * 32;
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
             const int colw = tn * BN + part * (BN / NPART) + lc4 * 4;
+            const bool fast = pitch_ok && (row_base + 32 <= M_rt) && (tn * BN + BN <= p.N);
+            const size_t row0 = (size_t)(row_base + lrow);     // this lane's first row in phase B
             auto load_aux = [&](int c) {
                 const int col = colw + c * CW;
+                if (fast) {
+                    if (kAuxF32) {
+                        const float* ap = reinterpret_cast<const float*>(p.aux) + row0 * p.ld_aux + col;
+#pragma unroll
+                        for (int it = 0; it < NIT; ++it) axf_n[it] = *reinterpret_cast<const float4*>(ap + it * aux_step);
+                    }
+                    if (kAuxBf16) {
+                        const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row0 * p.ld_aux + col;
+#pragma unroll
+                        for (int it = 0; it < NIT; ++it) axh_n[it] = *reinterpret_cast<const uint2*>(ap + it * aux_step);
+                    }
+                    return;
+                }
                 const int nvalid = p.N - col;
                 if (kAuxF32) {
 #pragma unroll
@@ -384,6 +406,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             };
             load_aux(0);
+            if (kAuxF32) {          // DropPath scale of each of this lane's rows: once per tile, not once per chunk
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const int row = row_base + it * RPA + lrow;
+                    rsc[it] = (p.row_scale != nullptr && row < M_rt) ? p.row_scale[row / p.scale_group] : 1.0f;
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -414,11 +443,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
                 // ---- phase B
-                if (nvalid > 0) {
+                if (fast) {
+                    auto ldv = [&](int it) {
+                        const int rr = it * RPA + lrow;
+                        const uint4 raw = *reinterpret_cast<const uint4*>(stg + rr * RB + (slot(rr, lc4) << 4));
+                        return make_float4(fmaf(__uint_as_float(raw.x), p.alpha, b4.x), fmaf(__uint_as_float(raw.y), p.alpha, b4.y),
+                                           fmaf(__uint_as_float(raw.z), p.alpha, b4.z), fmaf(__uint_as_float(raw.w), p.alpha, b4.w));
+                    };
+                    auto st_bf16 = [](__nv_bfloat16* q, const float4& v) {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                        *reinterpret_cast<uint2*>(q) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    };
+                    if constexpr (EPI == EPI_ATOMIC) {
+                        float* dp = reinterpret_cast<float*>(p.D) + row0 * p.ldd + col;
+#pragma unroll
+                        for (int it = 0; it < NIT; ++it) {
+                            const float4 v = ldv(it);
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dp + it * d_step), "f"(v.x),
+                                         "f"(v.y), "f"(v.z), "f"(v.w)
+                                         : "memory");
+                        }
+                    } else if constexpr (EPI == EPI_RESIDUAL) {
+                        float* dp = reinterpret_cast<float*>(p.D) + row0 * p.ldd + col;
+#pragma unroll
+                        for (int it = 0; it < NIT; ++it) {
+                            float4 v = ldv(it);
+                            const float4 a = axf_c[kAuxF32 ? it : 0];
+                            const float sc = rsc[kAuxF32 ? it : 0];
+                            v.x = fmaf(sc, v.x, a.x); v.y = fmaf(sc, v.y, a.y);
+                            v.z = fmaf(sc, v.z, a.z); v.w = fmaf(sc, v.w, a.w);
+                            *reinterpret_cast<float4*>(dp + it * d_step) = v;
+                        }
+                    } else if (p.out_f32) {          // EPI_STORE / EPI_GELU_BWD with fp32 output (fp32 GELU: generic path)
+                        float* dp = reinterpret_cast<float*>(p.D) + row0 * p.ldd + col;
+#pragma unroll
+                        for (int it = 0; it < NIT; ++it) {
+                            float4 v = ldv(it);
+                            if (EPI == EPI_GELU_BWD) v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                            *reinterpret_cast<float4*>(dp + it * d_step) = v;
+                        }
+                    } else {
+                        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + row0 * p.ldd + col;
+                        if (EPI == EPI_GELU && p.out2 != nullptr) {
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + row0 * p.ld_out2 + col;
+#pragma unroll
+                            for (int it = 0; it < NIT; ++it) {
+                                float4 v = ldv(it);
+                                const float4 d = gelu4_and_grad_fast(v);
+                                st_bf16(op + it * o2_step, d);
+                                st_bf16(dp + it * d_step, v);
+                            }
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < NIT; ++it) {
+                                float4 v = ldv(it);
+                                if (EPI == EPI_GELU) v = gelu4_fast(v);
+                                if (EPI == EPI_GELU_BWD) v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                                st_bf16(dp + it * d_step, v);
+                            }
+                        }
+                    }
+                } else if (nvalid > 0) {
                     const bool vD = vec && (p.ldd % 4 == 0), v2 = vec && (p.ld_out2 % 4 == 0);
                     // static register indexing of the prefetched aux operand needs the full unroll; the other
                     // epilogues keep the loop rolled up (instruction-cache footprint)
-#pragma unroll(kAuxF32 || kAuxBf16 ? NIT : 4)
+#pragma unroll(kAuxF32 || kAuxBf16 ? NIT : 1)
                     for (int it = 0; it < NIT; ++it) {
                         const int rr = it * RPA + lrow;
                         const int row = row_base + rr;
@@ -440,10 +529,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 v = gelu4_fast(v);
                             }
                         } else if (EPI == EPI_RESIDUAL) {
-                            const float rsc = p.row_scale != nullptr ? p.row_scale[row / p.scale_group] : 1.0f;
+                            const float rs = rsc[kAuxF32 ? it : 0];
                             const float4 a = axf_c[kAuxF32 ? it : 0];
-                            v.x = fmaf(rsc, v.x, a.x); v.y = fmaf(rsc, v.y, a.y);
-                            v.z = fmaf(rsc, v.z, a.z); v.w = fmaf(rsc, v.w, a.w);
+                            v.x = fmaf(rs, v.x, a.x); v.y = fmaf(rs, v.y, a.y);
+                            v.z = fmaf(rs, v.z, a.z); v.w = fmaf(rs, v.w, a.w);
                         } else if (EPI == EPI_GELU_BWD) {
                             v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
                         }

@@ -290,7 +290,7 @@ class EditorEngine:
         self._wgrad32(dqkv, sv["ln1"], bp.qkv, rows)
         lib.layernorm_bwd(dln, sv["x"], sv["m1"], sv["r1"], bp.ln1.g, g, g, None, bp.ln1.gg, bp.ln1.gb, dcol_prev, rows)
 
-    def _block_fwd(self, x, x1, x2, rows, bp, attn, tag, prec, rs_attn=None, rs_mlp=None, group=1, rd=None):
+    def _block_fwd(self, x, x1, x2, rows, bp, attn, tag, prec, rs_attn=None, rs_mlp=None, group=1, rd=None, keep=True):
         """One transformer block (vit_pytorch.py:215-220 / :311-317,328-329) on `rows` packed token rows.
         x, x1, x2: fp32 residual stream before / after attention / after MLP.  Returns what the backward needs."""
         ws, cap = self.ws, x.shape[0]
@@ -306,7 +306,9 @@ class EditorEngine:
         ln2 = ws.get(tag + "ln2", (cap, DIM), adt)
         m2, r2 = ws.get(tag + "m2", (cap,), torch.float32), ws.get(tag + "r2", (cap,), torch.float32)
         lib.layernorm_fwd(x1, bp.ln2.g, bp.ln2.b, bp.ln2.eps, ln2, m2, r2, rows, rows_dev=rd)
-        pre = ws.get(tag + "pre", (cap, HID), adt)
+        # "pre": bf16 mode -> gelu'(pre-activation), written by the fc1 epilogue for the backward (skipped when nothing
+        # is kept); fp32-faithful mode -> the pre-activation itself (edb_gelu_bwd_f32 differentiates it exactly)
+        pre = ws.get(tag + "pre", (cap, HID), adt) if (keep or prec != BF16) else None
         h = ws.get(tag + "h", (cap, HID), adt)
         self._linear(ln2, bp.fc1, h, rows, prec, epi=lib.EPI_GELU, out2=pre, rd=rd)
         self._linear(h, bp.fc2, x2, rows, prec, epi=lib.EPI_RESIDUAL, aux=x1, row_scale=rs_mlp, group=group, rd=rd)
@@ -378,7 +380,7 @@ class EditorEngine:
             rs_a = rs_m = None
             if droppath is not None:
                 rs_a, rs_m = droppath[2 * l], droppath[2 * l + 1]
-            sv = self._block_fwd(x, x1, x2, R, bp, attn, tag, prec, rs_a, rs_m, NTOK)
+            sv = self._block_fwd(x, x1, x2, R, bp, attn, tag, prec, rs_a, rs_m, NTOK, keep=keep)
             if keep:
                 saved.append(sv)
             x = x2
@@ -538,7 +540,8 @@ class EditorEngine:
         x1all = ws.get("hma_x1", (3, cap, DIM), torch.float32)
         saved = []
         for m in range(3):
-            saved.append(self._block_fwd(xp[m], x1all[m], x2all[m], T, self.hma_blocks[m], afwd, "hma%d_" % m, prec, rd=td))
+            saved.append(self._block_fwd(xp[m], x1all[m], x2all[m], T, self.hma_blocks[m], afwd, "hma%d_" % m, prec, rd=td,
+                                          keep=training))
         cls_mid = None
         if training:
             cls_mid = torch.empty(3, B, DIM, dtype=torch.float32, device=dev)
@@ -550,7 +553,7 @@ class EditorEngine:
         jfwd, jbwd = self._varlen_attn(sel["seq_off3"], B, 3 * ml, "hmaPj", prec, 3 * T)
         xj1 = ws.get("hma_xj1", (3 * cap, DIM), torch.float32)
         xj2 = ws.get("hma_xj2", (3 * cap, DIM), torch.float32)
-        svj = self._block_fwd(xj, xj1, xj2, 3 * T, self.hma_blocks[3], jfwd, "hmaJ_", prec, rd=t3d)
+        svj = self._block_fwd(xj, xj1, xj2, 3 * T, self.hma_blocks[3], jfwd, "hmaJ_", prec, rd=t3d, keep=training)
         xo = ws.get("hma_xo", (3 * cap, DIM), torch.float32)
         mo, ro = ws.get("hma_mo", (3 * cap,), torch.float32), ws.get("hma_ro", (3 * cap,), torch.float32)
         lib.layernorm_fwd(xj2, self.hma_out.g, self.hma_out.b, self.hma_out.eps, xo, mo, ro, 3 * T, rows_dev=t3d)

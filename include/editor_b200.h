@@ -38,9 +38,10 @@ extern "C" {
 
 /* GEMM epilogues */
 #define EPI_STORE 0    /* D = alpha*acc + bias                                                     */
-#define EPI_GELU 1     /* out2 = acc + bias (optional), D = gelu_erf(acc + bias)    (vit_pytorch.py:139-145) */
+#define EPI_GELU 1     /* D = gelu_erf(pre), pre = acc + bias (vit_pytorch.py:139-145); optional out2: bf16 D -> out2 =
+                        * gelu'(pre), the factor EPI_GELU_BWD multiplies by; fp32 D (EDB_PREC_FP32) -> out2 = pre         */
 #define EPI_RESIDUAL 2 /* D(f32) = aux(f32) + acc + bias; D may alias aux           (vit_pytorch.py:217-219) */
-#define EPI_GELU_BWD 3 /* D = acc * gelu'(aux)                                                      */
+#define EPI_GELU_BWD 3 /* D = acc * aux, aux = the bf16 gelu'(pre) saved by EPI_GELU (backward of nn.GELU)       */
 #define EPI_ATOMIC 4   /* D(f32) += acc   (split-K partial sums, D pre-zeroed by the caller)        */
 
 int edb_version(void);

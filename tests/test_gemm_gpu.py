@@ -42,12 +42,41 @@ def test_gemm_bias_gelu_bf16_out():
     bias = torch.randn(N, device="cuda") * 0.1
     D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
     pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    lib.gemm(A, B, D, M, N, K, epilogue=lib.EPI_GELU, bias=bias, out2=pre)
+    lib.gemm(A, B, D, M, N, K, epilogue=lib.EPI_GELU, bias=bias, out2=pre)      # bf16: out2 = gelu'(pre)
+    D1 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    lib.gemm(A, B, D1, M, N, K, epilogue=lib.EPI_GELU, bias=bias)                # eval: no second output
     torch.cuda.synchronize()
-    ref_pre = A.float() @ B.float().t() + bias
+    ref_pre = (A.float() @ B.float().t() + bias).requires_grad_(True)
     ref = torch.nn.functional.gelu(ref_pre)
-    assert (pre.float() - ref_pre).abs().max().item() < 2e-2
-    assert (D.float() - ref).abs().max().item() < 2e-2
+    ref.sum().backward()
+    assert (pre.float() - ref_pre.grad).abs().max().item() < 6e-3       # bf16 rounding of values up to 1.13: 4e-3
+    assert (D.float() - ref.detach()).abs().max().item() < 2e-2
+    assert (D1.float() - ref.detach()).abs().max().item() < 2e-2
+    # fp32 output (EDB_PREC_FP32): exact erf GELU and the pre-activation itself in out2
+    Df, pref = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    lib.gemm(A, B, Df, M, N, K, epilogue=lib.EPI_GELU, bias=bias, out2=pref)
+    torch.cuda.synchronize()
+    assert (pref - ref_pre.detach()).abs().max().item() < 2e-3
+    assert (Df - ref.detach()).abs().max().item() < 2e-3
+
+
+def test_gelu_epilogue_accuracy_over_the_whole_range():
+    """The one-tanh GELU / GELU' of the bf16 epilogues against exact erf GELU on a dense grid of pre-activations
+    (identity weights, so acc = x exactly): errors stay below half a bf16 ulp of the outputs."""
+    from editor_b200 import lib
+    M, N = 256, 256
+    x = torch.linspace(-12.0, 12.0, M * N, device="cuda").view(M, N).to(torch.bfloat16)
+    eye = torch.eye(N, device="cuda").to(torch.bfloat16)
+    g, d = (torch.empty(M, N, dtype=torch.bfloat16, device="cuda") for _ in range(2))
+    lib.gemm(x, eye, g, M, N, N, epilogue=lib.EPI_GELU, out2=d)
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(True)
+    ref = torch.nn.functional.gelu(xr)
+    ref.sum().backward()
+    eg = (g.double() - ref.detach()).abs() / (ref.detach().abs() * 2.0 ** -8 + 1e-3)
+    ed = (d.double() - xr.grad).abs() / (xr.grad.abs() * 2.0 ** -8 + 1e-3)
+    assert eg.max().item() < 1.0, eg.max().item()       # < 1 bf16 ulp (+1e-3 absolute floor near zero)
+    assert ed.max().item() < 1.0, ed.max().item()
 
 
 def test_gemm_residual_inplace():
@@ -66,13 +95,13 @@ def test_gemm_gelu_bwd_and_splitk():
     from editor_b200 import lib
     M, N, K = 640, 3072, 768
     dY, W = _mk(M, K, 7, 0.5), _mk(K, N, 8, 0.05)           # dH = dY @ W  (W stored [K_in=768 rows(k), N cols])
-    pre = _mk(M, N, 9)
+    x = _mk(M, N, 9).float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    dact = x.grad.to(torch.bfloat16)                         # the factor the forward epilogue saves
     D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    lib.gemm(dY, W, D, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=pre)
-    x = pre.float().requires_grad_(True)
-    torch.nn.functional.gelu(x).backward(dY.float() @ W.float())
+    lib.gemm(dY, W, D, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=dact)
     torch.cuda.synchronize()
-    assert (D.float() - x.grad).abs().max().item() < 3e-2
+    assert (D.float() - (dY.float() @ W.float()) * dact.float()).abs().max().item() < 3e-2
     # wgrad with split-K: dW[N', K'] = dY^T X, reduction over M rows
     Mr, Nw, Kw = 129 * 48, 768, 768
     dY2, X2 = _mk(Mr, Nw, 10, 0.1), _mk(Mr, Kw, 11, 0.1)

@@ -49,9 +49,9 @@ def main():
         rows.append((name, *res))
     add("qkv fwd  [M,768]x[2304,768] bias bf16", 2*M*2304*768, lambda: lib.gemm(x768, w_qkv, o2304, M, 2304, 768, bias=b2304))
     add("proj fwd [M,768]x[768,768] residual f32", 2*M*768*768, lambda: lib.gemm(x768, w_proj, res2, M, 768, 768, epilogue=lib.EPI_RESIDUAL, bias=b768, aux=res))
-    add("fc1 fwd  [M,768]x[3072,768] gelu + pre", 2*M*3072*768, lambda: lib.gemm(x768, w_fc1, o3072, M, 3072, 768, epilogue=lib.EPI_GELU, bias=b3072, out2=o3072b))
+    add("fc1 fwd  [M,768]x[3072,768] gelu + gelu'", 2*M*3072*768, lambda: lib.gemm(x768, w_fc1, o3072, M, 3072, 768, epilogue=lib.EPI_GELU, bias=b3072, out2=o3072b))
     add("fc2 fwd  [M,3072]x[768,3072] residual", 2*M*3072*768, lambda: lib.gemm(x3072, w_fc2, res2, M, 768, 3072, epilogue=lib.EPI_RESIDUAL, bias=b768, aux=res))
-    add("fc2 dgrad + gelu' -> [M,3072]", 2*M*3072*768, lambda: lib.gemm(x768, w_fc2, o3072, M, 3072, 768, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=x3072))
+    add("fc2 dgrad * saved gelu' -> [M,3072]", 2*M*3072*768, lambda: lib.gemm(x768, w_fc2, o3072, M, 3072, 768, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=x3072))
     add("fc1 dgrad -> [M,768]", 2*M*3072*768, lambda: lib.gemm(x3072, w_fc1, o768, M, 768, 3072, b_mn=True))
     add("proj dgrad -> [M,768]", 2*M*768*768, lambda: lib.gemm(x768, w_proj, o768, M, 768, 768, b_mn=True))
     add("qkv dgrad -> [M,768]", 2*M*2304*768, lambda: lib.gemm(x2304, w_qkv, o768, M, 768, 2304, b_mn=True))
