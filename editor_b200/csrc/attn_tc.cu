@@ -105,7 +105,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
             for (int c = 0; c < 3; ++c) tma_store_2d(&map_p, sP + c * AT_CHUNK_P, c * 64, blk * AT_L + 1);
             tma_store_commit();
-            tma_store_wait_all();
+            tma_store_wait_read();
         }
     } else if (warp == 5) {
         // ---------------- cls query (token 0) on CUDA cores

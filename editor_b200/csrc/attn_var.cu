@@ -111,7 +111,7 @@ attn_var_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) tma_store_2d(&map_p, sP + c * AV_QTILE, c * 64, sh * p.p_rows + qt * 128);
             tma_store_commit();
-            tma_store_wait_all();
+            tma_store_wait_read();
         }
     } else {
         const int i = threadIdx.x;

@@ -52,6 +52,7 @@ struct GemmKernelParams {
     int scale_group;
     const int* M_dev;   // optional: number of valid rows read on the device (packed HMA rows; no host sync)
     const int* K_dev;   // optional: reduction length read on the device (wgrad over packed rows)
+    float* colsum;      // optional (EPI_GELU_BWD): column sums of D accumulated with atomics (bias gradient)
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -443,6 +444,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
                 // ---- phase B
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);     // EPI_GELU_BWD: column sums of this lane's rows
                 if (fast) {
                     auto ldv = [&](int it) {
                         const int rr = it * RPA + lrow;
@@ -479,7 +481,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                         for (int it = 0; it < NIT; ++it) {
                             float4 v = ldv(it);
-                            if (EPI == EPI_GELU_BWD) v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                            if (EPI == EPI_GELU_BWD) {
+                                v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+                            }
                             *reinterpret_cast<float4*>(dp + it * d_step) = v;
                         }
                     } else {
@@ -498,7 +503,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             for (int it = 0; it < NIT; ++it) {
                                 float4 v = ldv(it);
                                 if (EPI == EPI_GELU) v = gelu4_fast(v);
-                                if (EPI == EPI_GELU_BWD) v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                                if (EPI == EPI_GELU_BWD) {
+                                    v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                                    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+                                }
                                 st_bf16(dp + it * d_step, v);
                             }
                         }
@@ -535,6 +543,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             v.z = fmaf(rs, v.z, a.z); v.w = fmaf(rs, v.w, a.w);
                         } else if (EPI == EPI_GELU_BWD) {
                             v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
                         }
                         if (EPI == EPI_ATOMIC) {
                             float* o = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
@@ -552,6 +561,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             st4g(reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col, v, nvalid, vD);
                         } else {
                             st4g(reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col, v, nvalid, vD);
+                        }
+                    }
+                }
+                if (EPI == EPI_GELU_BWD && p.colsum != nullptr) {
+                    // fused bias gradient: add up the RPA lanes that hold the same 4 columns, one vector red per chunk
+#pragma unroll
+                    for (int o = LPR; o < 32; o <<= 1) {
+                        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+                        cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+                        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+                        cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+                    }
+                    if (lrow == 0 && nvalid > 0) {
+                        float* o = p.colsum + col;
+                        if (nvalid >= 4) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(o), "f"(cs.x), "f"(cs.y),
+                                         "f"(cs.z), "f"(cs.w)
+                                         : "memory");
+                        } else {
+                            atomicAdd(o, cs.x);
+                            if (nvalid > 1) atomicAdd(o + 1, cs.y);
+                            if (nvalid > 2) atomicAdd(o + 2, cs.z);
                         }
                     }
                 }
@@ -693,6 +724,9 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     p.out2 = g.out2; p.ld_out2 = g.ld_out2; p.alpha = g.alpha;
     p.row_scale = g.row_scale; p.scale_group = g.scale_group > 0 ? g.scale_group : 1;
     p.M_dev = g.M_dev; p.K_dev = g.K_dev;
+    p.colsum = g.colsum;
+    if (g.colsum != nullptr && g.epilogue != EPI_GELU_BWD)
+        return edb_set_error(EDB_ERR_UNSUPPORTED, "gemm: colsum is fused into the GELU-backward epilogue only");
     if (g.epilogue == EPI_RESIDUAL && (g.aux == nullptr || !g.aux_f32 || !g.out_f32))
         return edb_set_error(EDB_ERR_SHAPE, "gemm: the residual epilogue needs fp32 aux and fp32 output");
     if (g.epilogue == EPI_GELU_BWD && (g.aux == nullptr || g.aux_f32))

@@ -252,46 +252,68 @@ int ce_smooth(const float* logits, long long ld, const long long* label, int B, 
 }
 
 // ------------------------------------------------------------------------------------------ batch-hard soft-margin triplet
-// dist[i][j] = sqrt(max(|x_i|^2 + |x_j|^2 - 2 x_i.x_j, 1e-12)) in fp32 (euclidean_dist, triplet_loss.py:16-31)
+// Gram matrix in feature slices: part[z][i][j] = sum_{f in slice z} x_i[f] x_j[f]  (fp32).  The feature dimension is cut
+// into TR_SLICES slices (one CTA each per 16x16 tile) so that the 64 tiles of a 128-batch become 512 CTAs with short
+// dependent-load chains; the slices are added in a fixed order by the mining kernel (deterministic).
+constexpr int TR_SLICES = 8;
 __global__ void __launch_bounds__(256) pairdist_kernel(const float* __restrict__ x, long long ld, int B, int F,
-                                                       float* __restrict__ dist) {
-    __shared__ float xi[16][33], xj[16][33];
+                                                       float* __restrict__ part) {
+    __shared__ float xi[16][65], xj[16][65];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
-    float dot = 0.f, ni = 0.f, nj = 0.f;
-    for (int f0 = 0; f0 < F; f0 += 32) {
-        for (int t = threadIdx.x; t < 16 * 32; t += 256) {
-            const int r = t >> 5, c = t & 31;
+    const int per = ((F + TR_SLICES - 1) / TR_SLICES + 63) / 64 * 64;
+    const int fa = blockIdx.z * per, fb = min(F, fa + per);
+    float dot = 0.f;
+    for (int f0 = fa; f0 < fb; f0 += 64) {
+        for (int t = threadIdx.x; t < 16 * 64; t += 256) {
+            const int r = t >> 6, c = t & 63;
             const int gi = blockIdx.y * 16 + r, gj = blockIdx.x * 16 + r;
-            xi[r][c] = (gi < B && f0 + c < F) ? x[(size_t)gi * ld + f0 + c] : 0.f;
-            xj[r][c] = (gj < B && f0 + c < F) ? x[(size_t)gj * ld + f0 + c] : 0.f;
+            xi[r][c] = (gi < B && f0 + c < fb) ? x[(size_t)gi * ld + f0 + c] : 0.f;
+            xj[r][c] = (gj < B && f0 + c < fb) ? x[(size_t)gj * ld + f0 + c] : 0.f;
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float a = xi[ty][c], b = xj[tx][c];
-            dot += a * b; ni += a * a; nj += b * b;
-        }
+        for (int c = 0; c < 64; ++c) dot += xi[ty][c] * xj[tx][c];
         __syncthreads();
     }
-    if (i < B && j < B) dist[(size_t)i * B + j] = sqrtf(fmaxf(ni + nj - 2.f * dot, 1e-12f));
+    if (i < B && j < B) part[((size_t)blockIdx.z * B + i) * B + j] = dot;
 }
 
-// one CTA, thread i = anchor: hardest positive / negative, loss = mean log(1 + exp(-(d_an - d_ap))), and the two gradient
-// coefficients  cp = dL/d(d_ap) / d_ap,  cn = dL/d(d_an) / d_an   (0 where the clamp is active)
-__global__ void triplet_mine_kernel(const float* __restrict__ dist, const long long* __restrict__ label, int B,
-                                    float* __restrict__ loss, int* __restrict__ pidx, int* __restrict__ nidx,
-                                    float* __restrict__ cp, float* __restrict__ cn) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per anchor i: G = sum of the slices; dist[i][j] = sqrt(max(G_ii + G_jj - 2 G_ij, 1e-12)) (euclidean_dist,
+// triplet_loss.py:16-31); hardest positive / negative (first index on ties, like torch.max / torch.min);
+// loss = mean log(1 + exp(-(d_an - d_ap))), and the two gradient coefficients  cp = dL/d(d_ap) / d_ap,
+// cn = dL/d(d_an) / d_an   (0 where the clamp is active)
+__global__ void __launch_bounds__(128) triplet_mine_kernel(const float* __restrict__ part, const long long* __restrict__ label,
+                                                           int B, float* __restrict__ loss, int* __restrict__ pidx,
+                                                           int* __restrict__ nidx, float* __restrict__ cp,
+                                                           float* __restrict__ cn) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= B) return;
+    auto gram = [&](int a, int b) {
+        float g = 0.f;
+#pragma unroll
+        for (int z = 0; z < TR_SLICES; ++z) g += part[((size_t)z * B + a) * B + b];
+        return g;
+    };
     const long long li = label[i];
+    const float gii = gram(i, i);
     float ap = -INFINITY, an = INFINITY;
-    int p = i, n = i;
-    for (int j = 0; j < B; ++j) {
-        const float d = dist[(size_t)i * B + j];
+    int p = B, n = B;
+    for (int j = lane; j < B; j += 32) {
+        const float d = sqrtf(fmaxf(gii + gram(j, j) - 2.f * gram(i, j), 1e-12f));
         if (label[j] == li) { if (d > ap) { ap = d; p = j; } }
         else if (d < an) { an = d; n = j; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ap2 = __shfl_xor_sync(0xffffffffu, ap, o), an2 = __shfl_xor_sync(0xffffffffu, an, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, p, o), n2 = __shfl_xor_sync(0xffffffffu, n, o);
+        if (ap2 > ap || (ap2 == ap && p2 < p)) { ap = ap2; p = p2; }
+        if (an2 < an || (an2 == an && n2 < n)) { an = an2; n = n2; }
+    }
+    if (lane != 0) return;
+    if (p >= B) p = i;
+    if (n >= B) n = i;
     const float xv = an - ap;
     const float l = xv > 0.f ? log1pf(expf(-xv)) : -xv + log1pf(expf(xv));
     atomicAdd(loss, l / (float)B);
@@ -302,7 +324,8 @@ __global__ void triplet_mine_kernel(const float* __restrict__ dist, const long l
     cn[i] = an > 1.0e-6f ? dan / an : 0.f;
 }
 
-// grid B: dx_i = g * [ cp_i (x_i - x_p) + cn_i (x_i - x_n) + sum_{k: p_k = i} cp_k (x_i - x_k) + sum_{k: n_k = i} cn_k (x_i - x_k) ]
+// grid (B, ceil(F/256)): dx_i = g * [ cp_i (x_i - x_p) + cn_i (x_i - x_n) + sum_{k: p_k = i} cp_k (x_i - x_k)
+//                                     + sum_{k: n_k = i} cn_k (x_i - x_k) ]
 __global__ void __launch_bounds__(256) triplet_grad_kernel(const float* __restrict__ x, long long ld, int B, int F,
                                                            const int* __restrict__ pidx, const int* __restrict__ nidx,
                                                            const float* __restrict__ cp, const float* __restrict__ cn,
@@ -317,32 +340,32 @@ __global__ void __launch_bounds__(256) triplet_grad_kernel(const float* __restri
     __syncthreads();
     const int i = blockIdx.x;
     const float gs = g[0];
-    for (int f = threadIdx.x; f < F; f += 256) {
-        const float xi = x[(size_t)i * ld + f];
-        float acc = scp[i] * (xi - x[(size_t)sp[i] * ld + f]) + scn[i] * (xi - x[(size_t)sn[i] * ld + f]);
-        for (int k = 0; k < B; ++k) {
-            if (sp[k] == i) acc += scp[k] * (xi - x[(size_t)k * ld + f]);
-            if (sn[k] == i) acc += scn[k] * (xi - x[(size_t)k * ld + f]);
-        }
-        float* o = dx + (size_t)i * ldd + f;
-        *o = accumulate ? *o + gs * acc : gs * acc;
+    const int f = blockIdx.y * 256 + threadIdx.x;
+    if (f >= F) return;
+    const float xi = x[(size_t)i * ld + f];
+    float acc = scp[i] * (xi - x[(size_t)sp[i] * ld + f]) + scn[i] * (xi - x[(size_t)sn[i] * ld + f]);
+    for (int k = 0; k < B; ++k) {
+        if (sp[k] == i) acc += scp[k] * (xi - x[(size_t)k * ld + f]);
+        if (sn[k] == i) acc += scn[k] * (xi - x[(size_t)k * ld + f]);
     }
+    float* o = dx + (size_t)i * ldd + f;
+    *o = accumulate ? *o + gs * acc : gs * acc;
 }
 
-size_t triplet_workspace_bytes(int B) { return (size_t)B * B * 4 + (size_t)B * 16; }
+size_t triplet_workspace_bytes(int B) { return (size_t)TR_SLICES * B * B * 4 + (size_t)B * 16; }
 
 int triplet_fwd(const float* x, long long ld, const long long* label, int B, int F, float* loss, void* workspace,
                 size_t ws_bytes, cudaStream_t st) {
     if (B <= 0) return EDB_OK;
     if (ws_bytes < triplet_workspace_bytes(B)) return edb_set_error(EDB_ERR_WORKSPACE, "triplet: workspace too small");
     float* dist = static_cast<float*>(workspace);
-    int* pidx = reinterpret_cast<int*>(dist + (size_t)B * B);
+    int* pidx = reinterpret_cast<int*>(dist + (size_t)TR_SLICES * B * B);
     int* nidx = pidx + B;
     float* cp = reinterpret_cast<float*>(nidx + B);
     float* cn = cp + B;
-    pairdist_kernel<<<dim3((B + 15) / 16, (B + 15) / 16), 256, 0, st>>>(x, ld, B, F, dist);
+    pairdist_kernel<<<dim3((B + 15) / 16, (B + 15) / 16, TR_SLICES), 256, 0, st>>>(x, ld, B, F, dist);
     EDB_CHECK_LAUNCH();
-    triplet_mine_kernel<<<(B + 127) / 128, 128, 0, st>>>(dist, label, B, loss, pidx, nidx, cp, cn);
+    triplet_mine_kernel<<<(B + 3) / 4, 128, 0, st>>>(dist, label, B, loss, pidx, nidx, cp, cn);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }
@@ -351,11 +374,12 @@ int triplet_bwd(const float* x, long long ld, int B, int F, const void* workspac
                 long long ldd, int accumulate, cudaStream_t st) {
     if (B <= 0) return EDB_OK;
     const float* dist = static_cast<const float*>(workspace);
-    const int* pidx = reinterpret_cast<const int*>(dist + (size_t)B * B);
+    const int* pidx = reinterpret_cast<const int*>(dist + (size_t)TR_SLICES * B * B);
     const int* nidx = pidx + B;
     const float* cp = reinterpret_cast<const float*>(nidx + B);
     const float* cn = cp + B;
-    triplet_grad_kernel<<<B, 256, (size_t)B * 16, st>>>(x, ld, B, F, pidx, nidx, cp, cn, g, dx, ldd, accumulate);
+    triplet_grad_kernel<<<dim3(B, (F + 255) / 256), 256, (size_t)B * 16, st>>>(x, ld, B, F, pidx, nidx, cp, cn, g, dx, ldd,
+                                                                             accumulate);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }

@@ -324,10 +324,10 @@ class EditorEngine:
         if rd is not None:
             for buf, width in ((gb, DIM), (dpre, HID), (dqkv, 3 * DIM)):
                 lib.call("edb_zero_rows", buf.data_ptr(), width * 2, rd, 64, lib.stream_ptr())
-        lib.gemm(gb, bp.fc2.w16, dpre, rows, HID, DIM, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=sv["pre"], M_dev=rd)
+        # dpre = (gb @ W2) * gelu'(pre); the fc1 bias gradient (column sums of dpre) comes out of the same epilogue
+        lib.gemm(gb, bp.fc2.w16, dpre, rows, HID, DIM, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=sv["pre"], M_dev=rd,
+                 colsum=bp.fc1.gb)
         self._wgrad(gb, sv["h"], bp.fc2, rows, rd)
-        if bp.fc1.gb is not None:
-            lib.colsum(dpre, bp.fc1.gb, rows, HID)
         dln = ws.get("dln", (cap, DIM), torch.bfloat16)
         lib.gemm(dpre, bp.fc1.w16, dln, rows, DIM, HID, b_mn=True, M_dev=rd)
         self._wgrad(dpre, sv["ln2"], bp.fc1, rows, rd)

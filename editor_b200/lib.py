@@ -35,6 +35,7 @@ class GemmDesc(ctypes.Structure):
         ("split_k", c_int),
         ("row_scale", c_vp), ("scale_group", c_int),
         ("M_dev", c_vp), ("K_dev", c_vp),
+        ("colsum", c_vp),
     ]
 
 
@@ -153,7 +154,7 @@ def gemm_set_mode(mode):
 
 
 def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None, aux=None, out2=None,
-         alpha=1.0, split_k=1, row_scale=None, scale_group=1, M_dev=None, K_dev=None):
+         alpha=1.0, split_k=1, row_scale=None, scale_group=1, M_dev=None, K_dev=None, colsum=None):
     """D[M,N] = epi(sum_k A(m,k) B(n,k)); A/B bf16 CUDA tensors, D bf16 or fp32 (2-D, row pitch = stride(0))."""
     d = GemmDesc()
     d.M, d.N, d.K = M, N, K
@@ -171,6 +172,7 @@ def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None
     d.row_scale = row_scale.data_ptr() if row_scale is not None else None
     d.scale_group = scale_group
     d.M_dev, d.K_dev = M_dev, K_dev
+    d.colsum = colsum.data_ptr() if colsum is not None else None
     if gemm_timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -99,9 +99,18 @@ def test_gemm_gelu_bwd_and_splitk():
     torch.nn.functional.gelu(x).sum().backward()
     dact = x.grad.to(torch.bfloat16)                         # the factor the forward epilogue saves
     D = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    lib.gemm(dY, W, D, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=dact)
+    csum = torch.full((N,), 0.5, device="cuda")             # fused bias gradient: ACCUMULATES the column sums of D
+    lib.gemm(dY, W, D, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=dact, colsum=csum)
     torch.cuda.synchronize()
-    assert (D.float() - (dY.float() @ W.float()) * dact.float()).abs().max().item() < 3e-2
+    refD = (dY.float() @ W.float()) * dact.float()
+    assert (D.float() - refD).abs().max().item() < 3e-2
+    assert (csum - 0.5 - refD.sum(0)).abs().max().item() < 2e-3 * refD.abs().sum(0).max().item()
+    # ragged rows (device-side row count): rows beyond it contribute nothing
+    m_dev = torch.tensor([M - 77], dtype=torch.int32, device="cuda")
+    csum2 = torch.zeros(N, device="cuda")
+    lib.gemm(dY, W, D, M, N, K, b_mn=True, epilogue=lib.EPI_GELU_BWD, aux=dact, colsum=csum2, M_dev=m_dev.data_ptr())
+    torch.cuda.synchronize()
+    assert (csum2 - refD[:M - 77].sum(0)).abs().max().item() < 2e-3 * refD.abs().sum(0).max().item()
     # wgrad with split-K: dW[N', K'] = dY^T X, reduction over M rows
     Mr, Nw, Kw = 129 * 48, 768, 768
     dY2, X2 = _mk(Mr, Nw, 10, 0.1), _mk(Mr, Kw, 11, 0.1)
