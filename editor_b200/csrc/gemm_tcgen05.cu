@@ -52,7 +52,7 @@ struct GemmKernelParams {
     int scale_group;
     const int* M_dev;   // optional: number of valid rows read on the device (packed HMA rows; no host sync)
     const int* K_dev;   // optional: reduction length read on the device (wgrad over packed rows)
-    float* colsum;      // optional (EPI_GELU_BWD): column sums of D accumulated with atomics (bias gradient)
+    float* colsum;      // optional (EPI_STORE / EPI_GELU_BWD): column sums of D accumulated with atomics (bias gradient)
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -336,6 +336,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         constexpr int RB = CW * 4;             // bytes per patch row
         constexpr bool kAuxF32 = (EPI == EPI_RESIDUAL);
         constexpr bool kAuxBf16 = (EPI == EPI_GELU_BWD);
+        constexpr bool kColsum = (EPI == EPI_GELU_BWD || EPI == EPI_STORE);   // fused bias gradient (optional)
         uint8_t* stg = smem + S::kStagingOffset + ew * (32 * RB);
         const int lrow = lane / LPR;           // phase B: row within a group of RPA
         const int lc4 = lane % LPR;            // phase B: which float4 of the chunk
@@ -481,10 +482,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                         for (int it = 0; it < NIT; ++it) {
                             float4 v = ldv(it);
-                            if (EPI == EPI_GELU_BWD) {
-                                v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
-                                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-                            }
+                            if (EPI == EPI_GELU_BWD) v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                            if (kColsum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
                             *reinterpret_cast<float4*>(dp + it * d_step) = v;
                         }
                     } else {
@@ -503,10 +502,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             for (int it = 0; it < NIT; ++it) {
                                 float4 v = ldv(it);
                                 if (EPI == EPI_GELU) v = gelu4_fast(v);
-                                if (EPI == EPI_GELU_BWD) {
-                                    v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
-                                    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-                                }
+                                if (EPI == EPI_GELU_BWD) v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
+                                if (kColsum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
                                 st_bf16(dp + it * d_step, v);
                             }
                         }
@@ -543,8 +540,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             v.z = fmaf(rs, v.z, a.z); v.w = fmaf(rs, v.w, a.w);
                         } else if (EPI == EPI_GELU_BWD) {
                             v = mul_bf16x4(v, axh_c[kAuxBf16 ? it : 0]);
-                            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
                         }
+                        if (kColsum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
                         if (EPI == EPI_ATOMIC) {
                             float* o = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col;
                             if (vD) {
@@ -564,7 +561,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                 }
-                if (EPI == EPI_GELU_BWD && p.colsum != nullptr) {
+                if (kColsum && p.colsum != nullptr) {
                     // fused bias gradient: add up the RPA lanes that hold the same 4 columns, one vector red per chunk
 #pragma unroll
                     for (int o = LPR; o < 32; o <<= 1) {
@@ -725,8 +722,8 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     p.row_scale = g.row_scale; p.scale_group = g.scale_group > 0 ? g.scale_group : 1;
     p.M_dev = g.M_dev; p.K_dev = g.K_dev;
     p.colsum = g.colsum;
-    if (g.colsum != nullptr && g.epilogue != EPI_GELU_BWD)
-        return edb_set_error(EDB_ERR_UNSUPPORTED, "gemm: colsum is fused into the GELU-backward epilogue only");
+    if (g.colsum != nullptr && g.epilogue != EPI_GELU_BWD && g.epilogue != EPI_STORE)
+        return edb_set_error(EDB_ERR_UNSUPPORTED, "gemm: colsum is fused into the store and GELU-backward epilogues only");
     if (g.epilogue == EPI_RESIDUAL && (g.aux == nullptr || !g.aux_f32 || !g.out_f32))
         return edb_set_error(EDB_ERR_SHAPE, "gemm: the residual epilogue needs fp32 aux and fp32 output");
     if (g.epilogue == EPI_GELU_BWD && (g.aux == nullptr || g.aux_f32))

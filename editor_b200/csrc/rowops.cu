@@ -207,7 +207,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, 
     const int c0 = blockIdx.x * 256 + lane * 8;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c0 < N) {
-        for (int r = blockIdx.y * 8 + warp; r < rows; r += gridDim.y * 8) {
+        const int step = gridDim.y * 8;
+        int r = blockIdx.y * 8 + warp;
+        for (; r + step < rows; r += 2 * step) {         // two rows in flight per warp
+            const T* p = src + (size_t)r * ld + c0;
+            const T* q = p + (size_t)step * ld;
+            const float4 a = load4(p), b = load4(p + 4), c = load4(q), d = load4(q + 4);
+            acc[0] += a.x + c.x; acc[1] += a.y + c.y; acc[2] += a.z + c.z; acc[3] += a.w + c.w;
+            acc[4] += b.x + d.x; acc[5] += b.y + d.y; acc[6] += b.z + d.z; acc[7] += b.w + d.w;
+        }
+        for (; r < rows; r += step) {
             const T* p = src + (size_t)r * ld + c0;
             const float4 a = load4(p), b = load4(p + 4);
             acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
@@ -229,9 +238,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, 
 int colsum(const void* src, long long ld, int src_f32, int rows, int N, float* out, cudaStream_t st) {
     if (rows <= 0 || N <= 0) return EDB_OK;
     if (N % 8 || ld % 8) return edb_set_error(EDB_ERR_ALIGN, "colsum: N and pitch must be multiples of 8");
+    const int gx = (N + 255) / 256;
     int splits = (rows + 255) / 256;
-    if (splits > 64) splits = 64;
-    dim3 grid((N + 255) / 256, splits);
+    const int cap = (4 * num_sms() + gx - 1) / gx;      // about four CTAs per SM over the whole grid
+    if (splits > cap) splits = cap;
+    dim3 grid(gx, splits);
     if (src_f32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)src, ld, rows, N, out);
     else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, ld, rows, N, out);
     EDB_CHECK_LAUNCH();

@@ -334,11 +334,18 @@ class EditorEngine:
         lib.layernorm_bwd(dln, sv["x1"], sv["m2"], sv["r2"], bp.ln2.g, g, g, gb, bp.ln2.gg, bp.ln2.gb, bp.proj.gb, rows,
                           row_scale=rs_attn, scale_group=group, rows_dev=rd)
         datt = ws.get("datt", (cap, DIM), torch.bfloat16)
-        lib.gemm(gb, bp.proj.w16, datt, rows, DIM, DIM, b_mn=True, M_dev=rd)
+        # qkv bias gradient without a pass over dqkv [rows, 2304]:
+        #   V part: sum_keys dV = sum_q dO_q (sum_k P_qk) = column sums of datt (softmax rows sum to 1) -> fused into the
+        #           epilogue of the proj dgrad GEMM that produces datt;
+        #   K part: sum_keys dK = sum_q Q_q (sum_k dS_qk) = 0 exactly (softmax is invariant to a per-query shift of the
+        #           scores, which is all a key bias does) -- autograd in the reference returns fp32 rounding noise here;
+        #   Q part: column sums of dqkv[:, :768] (a third of the matrix).
+        lib.gemm(gb, bp.proj.w16, datt, rows, DIM, DIM, b_mn=True, M_dev=rd,
+                 colsum=bp.qkv.gb[2 * DIM:] if bp.qkv.gb is not None else None)
         self._wgrad(gb, sv["att"], bp.proj, rows, rd)
         attn_bwd(sv["qkv"], sv["P"], datt, dqkv)
         if bp.qkv.gb is not None:
-            lib.colsum(dqkv, bp.qkv.gb, rows, 3 * DIM)
+            lib.colsum(dqkv, bp.qkv.gb, rows, DIM)
         lib.gemm(dqkv, bp.qkv.w16, dln, rows, DIM, 3 * DIM, b_mn=True, M_dev=rd)
         self._wgrad(dqkv, sv["ln1"], bp.qkv, rows, rd)
         lib.layernorm_bwd(dln, sv["x"], sv["m1"], sv["r1"], bp.ln1.g, g, g, gb, bp.ln1.gg, bp.ln1.gb, dcol_prev, rows,
@@ -647,9 +654,10 @@ class EditorEngine:
                 return self._reduce(cls_out, patch_mean, prec)
         self.arena.grad.zero_()
         dp = self._droppath(B, rgb.device)
-        tokens = _BackboneFn.apply(self, rgb, ni, ti, cam, prec, dp, *self.bb_plist)
-        tok = tokens.view(3, B, NTOK, DIM)
-        cls_bb = [tok[i, :, 0] for i in range(3)]
+        # the cls tokens leave the backbone as a second output: slicing `tokens` instead would make autograd materialise
+        # (zeros + scatter + add) a full [3B,129,768] gradient per slice -- 0.4 ms of fills and adds per step
+        tokens, cls3 = _BackboneFn.apply(self, rgb, ni, ti, cam, prec, dp, *self.bb_plist)
+        cls_bb = [cls3[i] for i in range(3)]
         lin, BN, LIN = self.tail_lin, _tail.BatchNormFn.apply, _tail.LinearFn.apply
         if m.AL:
             ori = torch.cat(cls_bb, dim=-1)
@@ -683,13 +691,23 @@ class _BackboneFn(torch.autograd.Function):
         eng.sel = eng.select(rgb, ni, ti, sv["maps"], prec, want_debug=eng.stats.get("debug", False))
         eng._mark("select_end")
         ctx.eng, ctx.sv, ctx.nparams, ctx.prec = eng, sv, len(params), prec
-        return tokens
+        B = rgb.shape[0]
+        cls3 = tokens.view(3, B, NTOK, DIM)[:, :, 0].contiguous()       # [3, B, 768]
+        return tokens, cls3
 
     @staticmethod
-    def backward(ctx, d_tokens):
+    def backward(ctx, d_tokens, d_cls3):
         eng = ctx.eng
         eng._mark("bb_bwd_start")
-        eng.backbone_backward(ctx.sv, d_tokens.contiguous().float())
+        if d_tokens is None:
+            B = d_cls3.shape[1]
+            d_tokens = torch.zeros(3 * B, NTOK, DIM, dtype=torch.float32, device=d_cls3.device)
+        else:
+            d_tokens = d_tokens.contiguous().float()
+        if d_cls3 is not None:
+            # d_tokens is the tensor our own HMA backward allocated (or the zeros above): add the cls rows in place
+            d_tokens.view(3, -1, NTOK, DIM)[:, :, 0] += d_cls3.float()
+        eng.backbone_backward(ctx.sv, d_tokens)
         eng._mark("bb_bwd_end")
         eng.arena.attach_grads(set(eng.bb_names))
         return (None,) * (7 + ctx.nparams)

@@ -65,9 +65,9 @@ typedef struct EdbGemmDesc {
     int scale_group;                   /* (vit_pytorch.py:52-69,217-219); NULL = 1.0                                      */
     const int* M_dev;                  /* optional DEVICE ints overriding M / K at run time (M, K then are upper bounds used  */
     const int* K_dev;                  /* for the launch): row counts of the packed HMA matrices are produced on the GPU     */
-    float* colsum;                     /* optional, EPI_GELU_BWD only: colsum[n] += sum_m D[m][n] (fp32, before the bf16    */
-                                       /* rounding of D) -- the bias gradient of the Linear whose output gradient D is        */
-                                       /* (vit_pytorch.py:133-136), fused so that D is not read back from HBM for it          */
+    float* colsum;                     /* optional, EPI_STORE / EPI_GELU_BWD: colsum[n] += sum_m D[m][n] (fp32, before the  */
+                                       /* bf16 rounding of D) -- the bias gradient of the Linear whose output gradient D is  */
+                                       /* (vit_pytorch.py:133-136), fused so that D is not read back from HBM for it         */
 } EdbGemmDesc;
 
 int edb_gemm_bf16(const EdbGemmDesc* desc, void* stream);
