@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -58,9 +58,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi takes ~0.1 s to initialise NVML (and holds driver locks while it does): it is started BEFORE the
+        warm-up and the timed region only begins once it is polling steadily, so that its start-up never lands inside."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -70,7 +77,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.2)]
+        for r in rows:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 6:
                 continue
@@ -196,23 +204,27 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    for _ in range(args.warmup):
-        trainer.step(xg, lg, cg)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        trainer.step(xg, lg, cg)
+    if rank == 0:
+        sampler.wait_first_sample()
+    barrier()
     n0 = lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         loss, _ = trainer.step(xg, lg, cg)
     e1.record()
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = lib.launch_count - n0
     n_sel = float(model.engine().last["num"].float().mean().item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     # ---- end to end ("e2e"): pinned host inputs -> H2D every step, loss read back every step
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

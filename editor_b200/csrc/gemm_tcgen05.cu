@@ -408,6 +408,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             };
             load_aux(0);
+            if (kAuxF32 || kAuxBf16) {
+                // the aux slab of this warp in the NEXT tile of this CTA goes to L2 now (one row per lane): by the time
+                // its chunks are fetched into registers (one chunk ahead) they come from L2, not from HBM -- the
+                // register prefetch alone left every chunk waiting on a DRAM round trip
+                const int wn = w + units;
+                if (wn < num_work) {
+                    int tm2, tn2, ks2;
+                    decode(wn, tm2, tn2, ks2);
+                    const int r2 = (tm2 * CG + (int)rank) * BM + quarter * 32 + lane;
+                    const int c2 = tn2 * BN + part * (BN / NPART);
+                    constexpr int kSlabCols = BN / NPART;
+                    const int esz = kAuxF32 ? 4 : 2;
+                    if (pitch_ok && r2 < M_rt && c2 + kSlabCols <= p.N && (p.ld_aux * esz) % 16 == 0)
+                        prefetch_l2_bulk(reinterpret_cast<const uint8_t*>(p.aux) + ((size_t)r2 * p.ld_aux + c2) * esz,
+                                         kSlabCols * esz);
+                }
+            }
             if (kAuxF32) {          // DropPath scale of each of this lane's rows: once per tile, not once per chunk
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
@@ -417,6 +434,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            uint32_t r[CW];
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 const int col_t = part * (BN / NPART) + c * CW;
@@ -431,10 +449,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int it = 0; it < NIT; ++it) axh_c[it] = axh_n[it];
                 }
-                // ---- phase A
-                uint32_t r[CW];
-                if constexpr (CW == 32) tmem_ld_32x32(t_base + col_t, r);
-                else tmem_ld_32x16(t_base + col_t, r);
+                // ---- phase A (the TMEM load of chunk c was issued during phase B of chunk c-1)
+                if (c == 0) {
+                    if constexpr (CW == 32) tmem_ld_32x32(t_base + col_t, r);
+                    else tmem_ld_32x16(t_base + col_t, r);
+                }
                 if (c + 1 < NCH) load_aux(c + 1);
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias != nullptr && EPI != EPI_ATOMIC && nvalid > 0) b4 = ld4g(p.bias + col, nvalid, vec);
@@ -443,6 +462,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int j = 0; j < LPR; ++j)
                     *reinterpret_cast<uint4*>(stg + lane * RB + (slot(lane, j) << 4)) =
                         make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                if (c + 1 < NCH) {          // next chunk's accumulator columns travel TMEM -> registers under phase B
+                    if constexpr (CW == 32) tmem_ld_32x32(t_base + col_t + CW, r);
+                    else tmem_ld_32x16(t_base + col_t + CW, r);
+                }
                 __syncwarp();
                 // ---- phase B
                 float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);     // EPI_GELU_BWD: column sums of this lane's rows
