@@ -162,7 +162,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
         for (int jj = 0; jj < 5; ++jj) {
             const int jn = (jj < 4) ? 32 : 1;
-            for (int t = 0; t < jn; ++t) {
+            _Pragma("unroll 8") for (int t = 0; t < jn; ++t) {
                 const int j = jj * 32 + t;
                 const float pj = __shfl_sync(0xffffffffu, sc[jj], t);
                 const float2 f = lds_bf162(sV + sw128(j, lane >> 2) + (lane & 3) * 4);
@@ -307,7 +307,10 @@ struct AttnTcBwdParams {
 // a 128-byte row of a swizzled smem tile (the contribution of the key / query that is not on the MMA tile)
 __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr, float a = 0.f, const uint8_t* tile = nullptr,
                                                  int line = 0) {
-#pragma unroll
+    // rolled on purpose (here and in the two dS passes below): the backward kernel is executed once per CTA, straight
+    // through; fully unrolled it was 150 KB of SASS -- more than the instruction cache -- and 17 % of its stall samples
+    // were instruction fetches
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
@@ -514,7 +517,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int jj = 0; jj < 5; ++jj) {
             const int jn = (jj < 4) ? 32 : 1;
-            for (int t = 0; t < jn; ++t) {
+            _Pragma("unroll 8") for (int t = 0; t < jn; ++t) {
                 const int j = jj * 32 + t;
                 const float dj = __shfl_sync(0xffffffffu, ds[jj], t);
                 const float2 f = lds_bf162(sK + sw128(j, lane >> 2) + (lane & 3) * 4);
@@ -537,7 +540,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int in = (ii < 4) ? 32 : 1;
-            for (int t = 0; t < in; ++t) {
+            _Pragma("unroll 8") for (int t = 0; t < in; ++t) {
                 const int i = ii * 32 + t;
                 const float pj = __shfl_sync(0xffffffffu, col[ii], t);
                 const float2 f = lds_bf162(sdO + sw128(i, lane >> 2) + (lane & 3) * 4);
@@ -557,7 +560,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
 #pragma unroll
         for (int ii = 0; ii < 5; ++ii) {
             const int in = (ii < 4) ? 32 : 1;
-            for (int t = 0; t < in; ++t) {
+            _Pragma("unroll 8") for (int t = 0; t < in; ++t) {
                 const int i = ii * 32 + t;
                 const float dj = __shfl_sync(0xffffffffu, col[ii], t);
                 const float2 f = lds_bf162(sQ + sw128(i, lane >> 2) + (lane & 3) * 4);
@@ -576,7 +579,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         mbar_wait(bar_dp, 0);
         tc_fence_after();
         float delta = p128 * dp128;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {            // 32 score columns per pass
             uint32_t r[32];
             tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
@@ -595,7 +598,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
         const float ds128 = __bfloat162float(__float2bfloat16(p128 * (dp128 - delta) * p.scale));
         dscol[i] = ds128;
         mbar_wait(bar_dv, 0);                    // P is no longer read by the dV MMA: overwrite it with dS
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
