@@ -8,6 +8,7 @@ A step is one training step (forward + loss + backward + gradient allreduce + SG
 RGBNT201 EDITOR.yml, ViT-B/16, batch 128 per GPU, bf16, synthetic RGB/NIR/TIR.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -49,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -214,6 +215,10 @@ def main():
         trainer.step(xg, lg, cg)
     for _ in range(args.warmup):
         trainer.step(xg, lg, cg)
+    # long-lived objects (model, arena views, workspace) leave the cyclic collector's young generations: a full collection
+    # landing inside the timed region cost one step ~18 ms (step_ms_each showed 57.9 ms once in eight)
+    gc.collect()
+    gc.freeze()
     if rank == 0:
         sampler.wait_first_sample()
     barrier()

@@ -387,11 +387,13 @@ int joint_gather(float* mod, long long cap, float* joint, const int* seq_off, in
 
 // ------------------------------------------------------------------------------------------ pooling (make_model.py:186-203)
 // x: joint layout after out_norm.  cls_out/patch_mean: [3][B][768];  num[b] = #RGB patch rows with sum != 0.
+// grid (B, 3): one CTA per (sample, modality); every CTA recounts the RGB rows (55 x 768 floats), four rows in flight
+// per thread in the column sums
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, const int* __restrict__ seq_off, int B,
                                                        float* __restrict__ cls_out, float* __restrict__ patch_mean,
                                                        int* __restrict__ num) {
     __shared__ int cnt;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, m = blockIdx.y;
     const int off = seq_off[b], len = seq_off[b + 1] - off;
     const float* base = x + (size_t)3 * off * DT;
     if (threadIdx.x == 0) cnt = 0;
@@ -400,6 +402,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__
     for (int r = 1 + warp; r < len; r += 8) {
         const float* row = base + (size_t)r * DT;
         float s = 0.f;
+#pragma unroll 4
         for (int c = lane; c < DT; c += 32) s += row[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -407,16 +410,21 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__
     }
     __syncthreads();
     const int n = cnt;
-    if (threadIdx.x == 0) num[b] = n;
+    if (threadIdx.x == 0 && m == 0) num[b] = n;
     const float inv = 1.0f / (float)n;   // n == 0 gives inf/nan exactly like the reference's division by zero
-    for (int m = 0; m < 3; ++m) {
-        const float* mb = base + (size_t)m * len * DT;
-        for (int c = threadIdx.x; c < DT; c += 256) {
-            float s = 0.f;
-            for (int r = 1; r < len; ++r) s += mb[(size_t)r * DT + c];
-            cls_out[((size_t)m * B + b) * DT + c] = mb[c];
-            patch_mean[((size_t)m * B + b) * DT + c] = s * inv;
+    const float* mb = base + (size_t)m * len * DT;
+    for (int c = threadIdx.x; c < DT; c += 256) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int r = 1;
+        for (; r + 3 < len; r += 4) {
+            s0 += mb[(size_t)r * DT + c];
+            s1 += mb[(size_t)(r + 1) * DT + c];
+            s2 += mb[(size_t)(r + 2) * DT + c];
+            s3 += mb[(size_t)(r + 3) * DT + c];
         }
+        for (; r < len; ++r) s0 += mb[(size_t)r * DT + c];
+        cls_out[((size_t)m * B + b) * DT + c] = mb[c];
+        patch_mean[((size_t)m * B + b) * DT + c] = ((s0 + s1) + (s2 + s3)) * inv;
     }
 }
 
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(192) pool_bwd_kernel(const float* __restrict__
 
 int pool_fwd(const float* x, const int* seq_off, int B, float* cls_out, float* patch_mean, int* num, cudaStream_t st) {
     if (B <= 0) return EDB_OK;
-    pool_fwd_kernel<<<B, 256, 0, st>>>(x, seq_off, B, cls_out, patch_mean, num);
+    pool_fwd_kernel<<<dim3(B, 3), 256, 0, st>>>(x, seq_off, B, cls_out, patch_mean, num);
     EDB_CHECK_LAUNCH();
     return EDB_OK;
 }
