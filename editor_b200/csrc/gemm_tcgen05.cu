@@ -19,6 +19,9 @@
 #include "ptx.cuh"
 #include "abi_internal.h"
 
+#ifndef EDB_AUX_PREFETCH
+#define EDB_AUX_PREFETCH 1      // next tile's aux slab -> L2: 0 = off, 1 = cp.async.bulk.prefetch.L2 per row, 2 = prefetch.global.L2 lines
+#endif
 #ifndef EDB_GELU_EPI_WARPS
 #define EDB_GELU_EPI_WARPS 16
 #endif
@@ -408,10 +411,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             };
             load_aux(0);
-            if (kAuxF32 || kAuxBf16) {
-                // the aux slab of this warp in the NEXT tile of this CTA goes to L2 now (one row per lane): by the time
-                // its chunks are fetched into registers (one chunk ahead) they come from L2, not from HBM -- the
-                // register prefetch alone left every chunk waiting on a DRAM round trip
+            if (kAuxBf16 && EDB_AUX_PREFETCH != 0) {
+                // the bf16 aux slab (saved gelu') of this warp in the NEXT tile of this CTA goes to L2 now (one row per
+                // lane): by the time its chunks are fetched into registers (one chunk ahead) they come from L2, not from
+                // HBM -- the register prefetch alone left every chunk waiting on a DRAM round trip.  A/B on one box
+                // (tools/gemm_bench.py): fc2 dgrad 0.255 -> 0.230 ms.  NOT done for the fp32 residual epilogues: there the
+                // same prefetch (512 B per row) cost 8 % (proj 0.087 -> 0.095 ms, fc2 fwd 0.165 -> 0.178 ms).
                 const int wn = w + units;
                 if (wn < num_work) {
                     int tm2, tn2, ks2;
@@ -420,9 +425,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int c2 = tn2 * BN + part * (BN / NPART);
                     constexpr int kSlabCols = BN / NPART;
                     const int esz = kAuxF32 ? 4 : 2;
-                    if (pitch_ok && r2 < M_rt && c2 + kSlabCols <= p.N && (p.ld_aux * esz) % 16 == 0)
-                        prefetch_l2_bulk(reinterpret_cast<const uint8_t*>(p.aux) + ((size_t)r2 * p.ld_aux + c2) * esz,
-                                         kSlabCols * esz);
+                    if (pitch_ok && r2 < M_rt && c2 + kSlabCols <= p.N && (p.ld_aux * esz) % 16 == 0) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) + ((size_t)r2 * p.ld_aux + c2) * esz;
+#if EDB_AUX_PREFETCH == 1
+                        prefetch_l2_bulk(src, kSlabCols * esz);
+#elif EDB_AUX_PREFETCH == 2
+#pragma unroll
+                        for (int b = 0; b < kSlabCols * esz; b += 128) prefetch_l2_line(src + b);
+#endif
+                    }
                 }
             }
             if (kAuxF32) {          // DropPath scale of each of this lane's rows: once per tile, not once per chunk

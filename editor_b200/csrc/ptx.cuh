@@ -119,6 +119,10 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// one 128-byte line into L2 through the load/store unit (no TMA request)
+__device__ __forceinline__ void prefetch_l2_line(const void* gptr) {
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gptr) : "memory");
+}
 // smem (swizzled tile) -> global through a tensor map; completion tracked by the bulk async-group
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
