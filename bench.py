@@ -321,6 +321,42 @@ def main():
         eval_rates[mode] = world * B * nrep / (a0.elapsed_time(a1) * 1e-3)
     model.precision = "auto"
     model.train()
+    # ---- secondary number: retrieval evaluation of one epoch -- RGBNT100-sized query / gallery sets of
+    # 2304-wide features: normalise + distance matrix + CMC / mAP on the GPU; the numpy oracle on a bounded query sample
+    eval_metrics = None
+    if rank == 0:
+        from editor_b200 import metrics as M
+        gq = torch.Generator(device="cpu").manual_seed(11)
+        nq, ng, nid = 1715, 8575, 50
+        feats = torch.randn(nq + ng, 2304, generator=gq)
+        pids = torch.randint(0, nid, (nq + ng,), generator=gq).numpy()
+        cams = torch.randint(0, 8, (nq + ng,), generator=gq).numpy()
+        fd = feats.to(device)
+        pq, pg = torch.from_numpy(pids[:nq]).to(device), torch.from_numpy(pids[nq:]).to(device)
+        cq, cg = torch.from_numpy(cams[:nq]).to(device), torch.from_numpy(cams[nq:]).to(device)
+
+        def run():
+            f = M.normalize_(fd.clone())
+            return M._rank(M.distmat_device(f[:nq], f[nq:]), pq, pg, cq, cg, 50)
+        run()
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        cmc_g, map_g = run()
+        m1.record()
+        torch.cuda.synchronize()
+        eval_metrics = {"queries": nq, "gallery": ng, "feature_dim": 2304, "gpu_ms": round(m0.elapsed_time(m1), 3),
+                        "mAP": map_g, "rank1": float(cmc_g[0])}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import eval_oracle as eo
+            ns = 128
+            t0 = time.perf_counter()
+            fn = eo.l2_normalize(feats.numpy())
+            d = eo.euclidean_distance(fn[:ns], fn[nq:])
+            eo.eval_func(d, pids[:ns], pids[nq:], cams[:ns], cams[nq:])
+            eval_metrics["cpu_oracle_ms_per_query"] = round((time.perf_counter() - t0) * 1e3 / ns, 3)
+            eval_metrics["cpu_sample"] = "oracle/eval_oracle.py on %d of the %d queries" % (ns, nq)
+        del fd
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -344,7 +380,8 @@ def main():
             "step_tflops_of_peak": {"algorithmic_gflop_per_image": step_gflop_img,
                                     "achieved_tflops_per_gpu": step_gflop_img * B / ms_step,
                                     "frac_of_peak": step_gflop_img * B / ms_step / peak_s},
-            "roofline": roof, "phase_ms": breakdown, "eval_forward_images_per_sec": eval_rates, "loss": float(loss_host)}
+            "roofline": roof, "phase_ms": breakdown, "eval_forward_images_per_sec": eval_rates, "eval_metrics": eval_metrics,
+            "loss": float(loss_host)}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, t_step = cpu_oracle_rate(4, 2, 1, sd)

@@ -158,4 +158,16 @@ int edb_triplet_bwd(const float* x, long long ld, int B, int F, const void* work
 }
 int edb_scale_by(const float* x, const float* a, float* y, size_t n, void* stream) { return edb::scale_by(x, a, y, n, ST); }
 
+
+int edb_eval_normalize(float* feats, long long ld, int n, int f, float eps, void* stream) {
+    return edb::eval_normalize(feats, ld, n, f, eps, ST);
+}
+int edb_eval_distmat(const float* qf, long long ldq, int q, const float* gf, long long ldg, int g, int f, float* dist,
+                     long long ldd, void* stream) {
+    return edb::eval_distmat(qf, ldq, q, gf, ldg, g, f, dist, ldd, ST);
+}
+int edb_eval_rank(const float* dist, long long ldd, int q, int g, const long long* q_pid, const long long* g_pid,
+                  const long long* q_key, const long long* g_key, double* ap, int* first_rank, int* overflow, void* stream) {
+    return edb::eval_rank(dist, ldd, q, g, q_pid, g_pid, q_key, g_key, ap, first_rank, overflow, ST);
+}
 }  // extern "C"

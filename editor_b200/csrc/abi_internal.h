@@ -88,4 +88,10 @@ int triplet_bwd(const float* x, long long ld, int B, int F, const void* workspac
                 long long ldd, int accumulate, cudaStream_t st);
 int scale_by(const float* x, const float* a, float* y, size_t n, cudaStream_t st);
 
+int eval_normalize(float* feats, long long ld, int N, int F, float eps, cudaStream_t st);
+int eval_distmat(const float* qf, long long ldq, int Q, const float* gf, long long ldg, int G, int F, float* dist,
+                 long long ldd, cudaStream_t st);
+int eval_rank(const float* dist, long long ldd, int Q, int G, const long long* q_pid, const long long* g_pid,
+              const long long* q_key, const long long* g_key, double* ap, int* first_rank, int* overflow, cudaStream_t st);
+
 }  // namespace edb

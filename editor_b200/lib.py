@@ -99,6 +99,9 @@ SIGNATURES = {
     "edb_triplet_fwd": (c_int, [c_vp, c_ll, c_vp, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "edb_triplet_bwd": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_int, c_vp]),
     "edb_scale_by": (c_int, [c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "edb_eval_normalize": (c_int, [c_vp, c_ll, c_int, c_int, c_float, c_vp]),
+    "edb_eval_distmat": (c_int, [c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_vp]),
+    "edb_eval_rank": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

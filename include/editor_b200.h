@@ -232,6 +232,22 @@ int edb_triplet_bwd(const float* x, long long ld, int B, int F, const void* work
 /* y[i] = a[0] * x[i] (a on the device): upstream-gradient scaling of a pre-computed gradient */
 int edb_scale_by(const float* x, const float* a, float* y, size_t n, void* stream);
 
+/* ---- retrieval evaluation (the step after the eval forward, utils/metrics.py) ------------------------ */
+
+/* feats[n][:] /= max(|feats[n]|_2, eps), in place: F.normalize(feats, dim=1, p=2) of R1_mAP_eval.compute
+ * (utils/metrics.py:255-256; eps = 1e-12 is torch's default) */
+int edb_eval_normalize(float* feats, long long ld, int n, int f, float eps, void* stream);
+/* dist[q][g] = |qf_q|^2 + |gf_g|^2 - 2 qf_q . gf_g, fp32: euclidean_distance (utils/metrics.py:12-18; squared, no sqrt) */
+int edb_eval_distmat(const float* qf, long long ldq, int q, const float* gf, long long ldg, int g, int f, float* dist,
+                     long long ldd, void* stream);
+/* eval_func (utils/metrics.py:133-191; key = camera id) / eval_func_msrv (:36-130; key = scene id) without the argsort:
+ * per query, gallery items with the query's pid AND key are removed; ap[q] = average precision (fp64), first_rank[q] =
+ * 1-based rank of the first correct match among the kept items, -1 when the query identity is absent from the gallery
+ * (the reference skips such queries).  Equal distances rank by ascending gallery index.  *overflow is incremented for
+ * queries with more than 2048 correct matches (not evaluated).  CMC[r] = mean_q [first_rank <= r+1], mAP = mean_q ap. */
+int edb_eval_rank(const float* dist, long long ldd, int q, int g, const long long* q_pid, const long long* g_pid,
+                  const long long* q_key, const long long* g_key, double* ap, int* first_rank, int* overflow, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
