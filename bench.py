@@ -187,7 +187,19 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL writes its banner ("NCCL version ...", and everything NCCL_DEBUG asks for) to stdout when the communicator
+        # is created: send that to stderr so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from editor_b200 import lib
     from editor_b200.train import Trainer
     lib.gemm_set_mode(args.gemm_mode)
