@@ -59,11 +59,6 @@ struct GemmKernelParams {
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
-}
 
 // bf16-output epilogues.  GELU and GELU' both come from ONE tanh.approx per element:
 //     Phi(x) = (1 + tanh(x P(x^2))) / 2,   P(t) = a + b t + c t^2 fitted to atanh(2 Phi(x) - 1) / x on |x| <= 4
