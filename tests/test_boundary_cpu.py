@@ -60,3 +60,33 @@ def test_product_path_fails_loudly_without_cuda():
     model, sd, x, label, cam, _ = ge._small_case(True, 2)
     with pytest.raises(lib.EdbError):
         model.eval()(x, cam_label=cam)
+
+
+def test_metrics_mirror_fails_loudly_without_cuda_and_keeps_the_reference_surface():
+    import inspect
+    import numpy as np
+    from editor_b200 import lib, metrics as M
+    # same names / arguments as utils/metrics.py:12,133,36,193,239 of the reference
+    assert list(inspect.signature(M.eval_func).parameters) == ["distmat", "q_pids", "g_pids", "q_camids", "g_camids", "max_rank"]
+    assert list(inspect.signature(M.eval_func_msrv).parameters)[:7] == ["distmat", "q_pids", "g_pids", "q_camids", "g_camids",
+                                                                        "q_sceneids", "g_sceneids"]
+    assert list(inspect.signature(M.R1_mAP_eval.__init__).parameters) == ["self", "num_query", "max_rank", "feat_norm", "reranking"]
+    for cls in (M.R1_mAP_eval, M.R1_mAP):
+        assert all(hasattr(cls, n) for n in ("reset", "update", "compute"))
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(lib.EdbError):
+        M.eval_func(np.zeros((1, 2), np.float32), np.array([1]), np.array([1, 2]), np.array([0]), np.array([1, 1]))
+    with pytest.raises(lib.EdbError):
+        M.euclidean_distance(np.zeros((1, 4), np.float32), np.zeros((2, 4), np.float32))
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under editor_b200/, modeling/ or config/ may import or execute it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle\.", re.M)
+    for top in ("editor_b200", "modeling", "config"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not pat.search(src), os.path.join(dirpath, f)
