@@ -22,6 +22,18 @@
 #ifndef EDB_AUX_PREFETCH
 #define EDB_AUX_PREFETCH 1      // next tile's aux slab -> L2: 0 = off, 1 = cp.async.bulk.prefetch.L2 per row, 2 = prefetch.global.L2 lines
 #endif
+// Experimental build switches for A/B runs on one box (make OUT=../lib_x EXTRA=-D...; EDB_LIB=.../lib_x/libeditor_b200.so
+// python tools/gemm_bench.py); both are OFF in the shipped library and have not been measured yet:
+//   EDB_BIAS_PRELOAD=1  the bias of chunk c+1 is fetched during chunk c (today every chunk waits for its own bias load:
+//                       long-scoreboard stalls at the first FFMA of phase B in profiles/r01_ncu_gemm_fc1.txt)
+//   EDB_WAIT_BACKOFF=n  producer / epilogue waits poll with n ns of nanosleep in between (the spin loops are ~10 % of the
+//                       issued instructions of the fc1 GEMM)
+#ifndef EDB_BIAS_PRELOAD
+#define EDB_BIAS_PRELOAD 0
+#endif
+#ifndef EDB_WAIT_BACKOFF
+#define EDB_WAIT_BACKOFF 0
+#endif
 #ifndef EDB_GELU_EPI_WARPS
 #define EDB_GELU_EPI_WARPS 16
 #endif
@@ -248,7 +260,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int kb0 = ks * kb_per_split;
                 const int kb1 = min(kb_total, kb0 + kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
+#if EDB_WAIT_BACKOFF > 0
+                    mbar_wait_backoff(&empty_bar[stage], phase ^ 1, EDB_WAIT_BACKOFF);
+#else
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+#endif
                     uint8_t* sa = smem + stage * S::kStageBytes;
                     uint8_t* sb = sa + S::kABytes;
                     // the leader's barrier collects the bytes of both CTAs
@@ -438,7 +454,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     rsc[it] = (p.row_scale != nullptr && row < M_rt) ? p.row_scale[row / p.scale_group] : 1.0f;
                 }
             }
+#if EDB_BIAS_PRELOAD
+            float4 b4n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && EPI != EPI_ATOMIC && p.N - colw > 0) b4n = ld4g(p.bias + colw, p.N - colw, p.N - colw >= 4);
+#endif
+#if EDB_WAIT_BACKOFF > 0
+            mbar_wait_backoff(&tmem_full[acc], acc_phase, EDB_WAIT_BACKOFF);
+#else
             mbar_wait(&tmem_full[acc], acc_phase);
+#endif
             tc_fence_after();
             uint32_t r[CW];
 #pragma unroll 1
@@ -461,8 +485,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     else tmem_ld_32x16(t_base + col_t, r);
                 }
                 if (c + 1 < NCH) load_aux(c + 1);
+#if EDB_BIAS_PRELOAD
+                const float4 b4 = b4n;
+                if (c + 1 < NCH) {
+                    const int nv2 = nvalid - CW;
+                    b4n = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias != nullptr && EPI != EPI_ATOMIC && nv2 > 0) b4n = ld4g(p.bias + col + CW, nv2, nv2 >= 4);
+                }
+#else
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias != nullptr && EPI != EPI_ATOMIC && nvalid > 0) b4 = ld4g(p.bias + col, nvalid, vec);
+#endif
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < LPR; ++j)

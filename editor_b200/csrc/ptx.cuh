@@ -69,6 +69,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// polling wait with a sleep between attempts: for waits whose wake-up latency does not matter (a producer with a deep
+// ring ahead of it, an epilogue warp waiting a whole tile for its accumulator) -- the try_wait loop above re-issues every
+// few hundred cycles and those instructions compete with the epilogue warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+    }
+}
+
 // ---------------------------------------------------------------- thread-block clusters (CTA pairs)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
