@@ -88,7 +88,7 @@ def summarize_launches():
     tot = sum(v[1] for v in agg.values())
     own = sum(v[1] for k, v in agg.items() if "edb::" in k)
     with open(os.path.join(OUT, "%s_launches_step.txt" % TAG), "w") as f:
-        f.write("# one training step (B=128, bf16) of `python bench.py --steps 1 --warmup 3` under\n"
+        f.write("# one training step (B=128, bf16; the last of `python tools/one_step.py 4`, or of bench.py in earlier rounds) under\n"
                 "# ncu --metrics gpu__time_duration.sum --clock-control none (per-launch times are cold-cache and serialised:\n"
                 "# compare SHARES).  %d launches, %.3f ms summed; editor_b200 kernels: %d launches, %.1f %% of the time.\n"
                 % (len(step), tot, sum(v[0] for k, v in agg.items() if "edb::" in k), 100 * own / tot))
