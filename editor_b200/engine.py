@@ -140,17 +140,34 @@ class Arena:
             lib.cast_bf16(self.flat, self.flat16, self.total)
             self._versions = vers
 
+    def prepare_grads(self):
+        """Called at the start of every training forward.  torch semantics: ``.grad`` ACCUMULATES until the caller zeroes
+        it (engine/processor.py:72 ``optimizer.zero_grad()``; gradient accumulation over micro-batches must keep working).
+        * every ``p.grad`` is None (``zero_grad(set_to_none=True)``, the torch default) -> one memset of the arena;
+        * ``p.grad`` is already the arena view -> left alone: the kernels accumulate on top (whoever zeroed the views in
+          place -- ``zero_grad(set_to_none=False)`` -- zeroed the arena);
+        * ``p.grad`` is a foreign tensor (assigned by the caller) -> its value is adopted into the arena once, here, and
+          ``p.grad`` re-pointed at the view, so the backward never has to add into it piecewise."""
+        if not any(p.grad is not None for p in self.params):
+            self.grad.zero_()
+            return
+        for name, p in zip(self.names, self.params):
+            gv = self.gview(name)
+            if p.grad is None:
+                gv.zero_()
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)
+                p.grad = gv
+
     def attach_grads(self, names=None):
         """Expose the gradient arena through ``p.grad`` (what GradScaler / torch optimizers of the unchanged caller
-        read, engine/processor.py:94-96)."""
+        read, engine/processor.py:94-96).  Idempotent: a parameter with several contributors per step (BACKBONE_HEAD /
+        BACKBONE_BN are called three times when AL = 0) is attached by the first one."""
         for name, p in zip(self.names, self.params):
             if names is not None and name not in names:
                 continue
-            gv = self.gview(name)
             if p.grad is None:
-                p.grad = gv
-            elif p.grad.data_ptr() != gv.data_ptr():
-                p.grad.add_(gv)
+                p.grad = self.gview(name)
 
 
 class Workspace:
@@ -613,10 +630,50 @@ class EditorEngine:
             return BF16 if (training or torch.is_autocast_enabled("cuda")) else FP32
         return p
 
+    def _check_cam(self, cam, B, training):
+        """`sie_embed[cam[b]]` is gathered by the embed kernel: range-check on the device (no host sync) on the first
+        forward of every (batch size, mode), or on every one with ``model.validate_inputs = True``."""
+        m = self.model
+        if cam.shape != (B,):
+            raise lib.EdbError("cam_label must have shape [%d]" % B)
+        seen = self.stats.setdefault("validated", set())
+        check = getattr(m, "validate_inputs", False) or (B, training) not in seen
+        seen.add((B, training))
+        cams = int(getattr(m.BACKBONE.base, "cam_num", 0))
+        if check and cams > 1:
+            torch._assert_async(((cam >= 0) & (cam < cams)).all(), "cam_label out of range [0, camera_num)")
+        return check
+
+    def _check_labels(self, label, B, device, check):
+        """The tail kernels index with these (`centers[label[b]]`, `logits[b][label[b]]`): int64, on the device,
+        contiguous, in range -- where the reference raises an index error we must not read out of bounds.  OCFR needs
+        P x K contiguous identities (OCFR.py:31-42 takes ``label_[::chunk]``; data/datasets/sampler.py delivers exactly
+        that)."""
+        if label is None:
+            raise lib.EdbError("the training forward needs `label` (make_model.py:150, OCFR.py:44)")
+        label = label.to(device=device, dtype=torch.int64).contiguous()
+        if label.shape != (B,):
+            raise lib.EdbError("label must have shape [%d]" % B)
+        if check:
+            C = self.model.FUSE_block.memory_cls.RGB_centers.shape[0]
+            torch._assert_async(((label >= 0) & (label < C)).all(), "label out of range [0, num_class)")
+            # OCFR.py:31-42 pairs row j with the centre of label_[(j // chunk) * chunk], chunk = B // #identities; the
+            # kernel pairs row j with the centre of its OWN label -- identical exactly when the following holds
+            srt = torch.sort(label).values
+            n_ids = (srt[1:] != srt[:-1]).sum() + 1
+            chunk = torch.div(B, n_ids, rounding_mode="floor")
+            j = torch.arange(B, device=device)
+            anchor = torch.div(j, chunk, rounding_mode="floor") * chunk
+            ok = (label[anchor] == label).all() & (B % chunk == 0)
+            torch._assert_async(ok, "labels are not P x K contiguous (OCFR.py:31-42: K instances per identity in a row)")
+        return label
+
     def _droppath(self, B, device):
-        """Per-sample keep/keep_prob factors in the reference's draw order: for each modality call (RGB, NI, TI), for
-        each block, one torch.rand((B,1,1)) for the attention branch then one for the MLP branch (vit_pytorch.py:52-69,
-        215-220; block 0 has rate 0 -> nn.Identity, :210).  Returned as 24 vectors of length 3B (sequence s = m*B+b)."""
+        """Per-sample keep/keep_prob factors, one vector of length 3B (sequence s = m*B+b) per residual branch: 24 vectors
+        from ONE torch.rand((24, 3B)) per step.  Same distribution as the reference (floor(keep_prob + U[0,1)) / keep_prob
+        per sample, per branch, per modality call; block 0 has rate 0 -> nn.Identity, vit_pytorch.py:52-69,210,215-220),
+        but NOT the same random stream: the reference draws torch.rand((B,1,1)) 23 x 3 times in call order, so seeded runs
+        agree in distribution only.  Parity tests inject the masks (test_droppath_matches_oracle) or set DROP_PATH 0."""
         rates = self.model.BACKBONE.base.drop_path_rates
         if max(rates) <= 0.0:
             return None
@@ -638,8 +695,9 @@ class EditorEngine:
         B = rgb.shape[0]
         if cam_label is None:
             cam_label = torch.zeros(B, dtype=torch.int64, device=rgb.device)
-        cam = cam_label.to(torch.int64).contiguous()
+        cam = cam_label.to(device=rgb.device, dtype=torch.int64).contiguous()
         training = m.training
+        check = self._check_cam(cam, B, training)
         prec = self._precision(training)
         # model.precision = "fp32" trains fp32-faithfully (every GEMM as a 3-piece bf16 split, fp32 attention): the parity
         # mode of BASELINE.json configs[4]; ~6x the tensor work of the bf16 mode
@@ -652,39 +710,71 @@ class EditorEngine:
                 cls_out, patch_mean, _, _, num, _ = self.hma_forward(tokens, sel, prec, False)
                 self.last = dict(tokens=tokens, num=num)
                 return self._reduce(cls_out, patch_mean, prec)
-        self.arena.grad.zero_()
+        ag = self.autograd_params()
+        if ag:
+            # autograd / DistributedDataParallel mode: the arena is scratch for ONE forward+backward, parameter gradients
+            # leave through the autograd graph (AccumulateGrad -> DDP reducer hooks), p.grad is torch's business
+            if self.stats.get("pending_backward"):
+                raise lib.EdbError("autograd (DDP) mode supports one backward per forward: a second training forward was "
+                                   "started before the backward of the previous one")
+            self.stats["pending_backward"] = True
+            self.arena.grad.zero_()
+        else:
+            self.arena.prepare_grads()
+        P = (lambda *names: tuple(self.arena.params[self.arena.names.index(n)] for n in names)) if ag else (lambda *n: ())
+        label = self._check_labels(label, B, rgb.device, check)
         dp = self._droppath(B, rgb.device)
         # the cls tokens leave the backbone as a second output: slicing `tokens` instead would make autograd materialise
         # (zeros + scatter + add) a full [3B,129,768] gradient per slice -- 0.4 ms of fills and adds per step
-        tokens, cls3 = _BackboneFn.apply(self, rgb, ni, ti, cam, prec, dp, *self.bb_plist)
+        tokens, cls3 = _BackboneFn.apply(self, rgb, ni, ti, cam, prec, dp, ag, *self.bb_plist)
         cls_bb = [cls3[i] for i in range(3)]
         lin, BN, LIN = self.tail_lin, _tail.BatchNormFn.apply, _tail.LinearFn.apply
         if m.AL:
             ori = torch.cat(cls_bb, dim=-1)
-            ori_score = LIN(self, lin["AL_HEAD"], prec, BN(self, "AL_BN", m.AL_BN, ori))
+            ori_score = LIN(self, lin["AL_HEAD"], prec, BN(self, "AL_BN", m.AL_BN, ori, *P("AL_BN.weight", "AL_BN.bias")),
+                            *P("AL_HEAD.weight"))
         else:   # three separate BN calls, each with its own batch statistics (SURVEY.md App. A-11)
-            scores = [LIN(self, lin["BACKBONE_HEAD"], prec, BN(self, "BACKBONE_BN", m.BACKBONE_BN, c)) for c in cls_bb]
-        cls_out, patch_mean, cls_mid, loss_bcc = _HMAFn.apply(self, tokens, prec, *self.hma_plist)
-        loss_ocfr = _tail.OcfrFn.apply(m.FUSE_block.memory_cls, cls_mid, label)
+            scores = [LIN(self, lin["BACKBONE_HEAD"], prec,
+                          BN(self, "BACKBONE_BN", m.BACKBONE_BN, c, *P("BACKBONE_BN.weight", "BACKBONE_BN.bias")),
+                          *P("BACKBONE_HEAD.weight")) for c in cls_bb]
+        cls_out, patch_mean, cls_mid, loss_bcc = _HMAFn.apply(self, tokens, prec, ag, *self.hma_plist)
+        loss_ocfr = _tail.OcfrFn.apply(m.FUSE_block.memory_cls, cls_mid, label)        # label: checked int64 above
         if writer is not None:
             writer.add_scalar("num_count", self.last["num"].float().mean(), epoch)      # make_model.py:199-200
-        cls4t = self._reduce(cls_out, patch_mean, prec)
-        score = LIN(self, lin["FUSE_HEAD"], prec, BN(self, "FUSE_BN", m.FUSE_BN, cls4t))
+        cls4t = self._reduce(cls_out, patch_mean, prec, P)
+        score = LIN(self, lin["FUSE_HEAD"], prec, BN(self, "FUSE_BN", m.FUSE_BN, cls4t, *P("FUSE_BN.weight", "FUSE_BN.bias")),
+                    *P("FUSE_HEAD.weight"))
         aux = loss_bcc.reshape(()) + loss_ocfr.reshape(())
         if m.AL:
             return score, cls4t, ori_score, ori, aux
         return score, cls4t, scores[0], cls_bb[0], scores[1], cls_bb[1], scores[2], cls_bb[2], aux
 
-    def _reduce(self, cls_out, patch_mean, prec):
+    def _reduce(self, cls_out, patch_mean, prec, P=lambda *n: ()):
         """*_REDUCE(cat(cls, patch mean)) and the concatenation to cls4t [B, 2304] (make_model.py:205-208)."""
-        outs = [_tail.LinearFn.apply(self, self.tail_lin[n], prec, torch.cat([cls_out[i], patch_mean[i]], dim=-1))
+        outs = [_tail.LinearFn.apply(self, self.tail_lin[n], prec, torch.cat([cls_out[i], patch_mean[i]], dim=-1),
+                                     *P(n + ".weight", n + ".bias"))
                 for i, n in enumerate(("RGB_REDUCE", "NIR_REDUCE", "TIR_REDUCE"))]
         return torch.cat(outs, dim=-1)
+
+    def autograd_params(self):
+        """True -> parameter gradients are RETURNED by the autograd Functions instead of being exposed as views of the
+        gradient arena.  Needed by ``torch.nn.parallel.DistributedDataParallel(find_unused_parameters=True)``
+        (engine/processor.py:47-50): its reducer listens on every parameter's AccumulateGrad node.  ``model.param_grads``:
+        "arena" (default single-process fast path, also what ``editor_b200.train.Trainer`` drives), "autograd", or
+        "auto" = autograd exactly when torch.distributed is initialised with more than one rank and no Trainer hook is
+        installed (i.e. somebody else -- DDP -- is responsible for the gradient exchange)."""
+        mode = getattr(self.model, "param_grads", "auto")
+        if mode == "auto":
+            import torch.distributed as dist
+            return bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                        and self.stats.get("grad_hook") is None)
+        return mode == "autograd"
 
 
 class _BackboneFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eng, rgb, ni, ti, cam, prec, dp, *params):
+    def forward(ctx, eng, rgb, ni, ti, cam, prec, dp, ag, *params):
+        ctx.ag = ag
         eng._mark("bb_fwd_start")
         tokens, sv = eng.backbone_forward(rgb, ni, ti, cam, prec, keep=True, droppath=dp)
         eng._mark("bb_fwd_end")
@@ -709,13 +799,17 @@ class _BackboneFn(torch.autograd.Function):
             d_tokens.view(3, -1, NTOK, DIM)[:, :, 0] += d_cls3.float()
         eng.backbone_backward(ctx.sv, d_tokens)
         eng._mark("bb_bwd_end")
+        eng.stats["pending_backward"] = False
+        if ctx.ag:      # clones: AccumulateGrad may keep the tensor it is handed as p.grad, the arena is reused next step
+            return (None,) * 8 + tuple(eng.arena.gview(n).clone() for n in eng.bb_names)
         eng.arena.attach_grads(set(eng.bb_names))
-        return (None,) * (7 + ctx.nparams)
+        return (None,) * (8 + ctx.nparams)
 
 
 class _HMAFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eng, tokens, prec, *params):
+    def forward(ctx, eng, tokens, prec, ag, *params):
+        ctx.ag = ag
         eng._mark("hma_fwd_start")
         cls_out, patch_mean, cls_mid, loss_bcc, num, sv = eng.hma_forward(tokens, eng.sel, prec, True)
         eng._mark("hma_fwd_end")
@@ -735,5 +829,7 @@ class _HMAFn(torch.autograd.Function):
                                     None if d_mid is None else d_mid.contiguous().float(),
                                     None if d_bcc is None else d_bcc.contiguous().float())
         eng._mark("hma_bwd_end")
+        if ctx.ag:
+            return (None, d_tokens, None, None) + tuple(eng.arena.gview(n).clone() for n in eng.hma_names)
         eng.arena.attach_grads(set(eng.hma_names))
-        return (None, d_tokens, None) + (None,) * ctx.nparams
+        return (None, d_tokens, None, None) + (None,) * ctx.nparams

@@ -142,7 +142,8 @@ def _f32(t):
 
 
 launch_count = 0   # kernels launched through the C ABI (bench.py reports it as gpu_launches)
-gemm_timing = None  # bench.py sets this to a list to collect (flops, start_event, end_event) per GEMM launch
+gemm_timing = None  # bench.py sets this to a list to collect one record (shape, device-side row count pointers, CUDA
+#                     events) per GEMM launch; FLOPs / bytes are computed from the ACTUAL row counts after the step
 
 
 def call(name, *args):
@@ -181,8 +182,11 @@ def gemm(A, B, D, M, N, K, a_mn=False, b_mn=False, epilogue=EPI_STORE, bias=None
         e0.record()
         call("edb_gemm_bf16", ctypes.byref(d), stream_ptr())
         e1.record()
-        gemm_timing.append((2.0 * M * N * K, e0, e1, "%dx%dx%d %s%s epi%d%s" % (
-            M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", epilogue, " sk%d" % split_k if split_k > 1 else "")))
+        esz = lambda t: 0 if t is None else t.element_size()          # noqa: E731
+        gemm_timing.append({"M": M, "N": N, "K": K, "M_dev": M_dev, "K_dev": K_dev, "e0": e0, "e1": e1,
+                            "out_bytes_per_elem": esz(D) + esz(aux) + esz(out2),
+                            "key": "%dx%dx%d %s%s epi%d%s" % (M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", epilogue,
+                                                              " sk%d" % split_k if split_k > 1 else "")})
         return D
     call("edb_gemm_bf16", ctypes.byref(d), stream_ptr())
     return D

@@ -16,7 +16,11 @@ class LinearFn(torch.autograd.Function):
     """y = x W^T (+ b) for one of the small tail linears; W, b live in the parameter arena (L is an engine._Lin)."""
 
     @staticmethod
-    def forward(ctx, eng, L, prec, x):
+    def forward(ctx, eng, L, prec, x, *params):
+        """params: () in the arena mode (gradients are written into the flat gradient arena and exposed through
+        ``p.grad``), or (W[, b]) in the autograd mode (``engine.EditorEngine.autograd_params``: DistributedDataParallel
+        needs every parameter gradient to come out of the autograd graph) -- then the backward RETURNS them."""
+        ctx.nparams = len(params)
         B, K, N = x.shape[0], L.in_f, L.out_f
         x = x.contiguous().float()
         y = torch.empty(B, _pad8(N), dtype=torch.float32, device=x.device)
@@ -29,6 +33,7 @@ class LinearFn(torch.autograd.Function):
             lib.split3(x, xb, 0)
             lib.gemm(xb, L.wsplit(), y, B, N, 6 * K, bias=L.b)
         ctx.eng, ctx.L, ctx.xb, ctx.prec, ctx.x32 = eng, L, xb, prec, (x if prec != BF16 else None)
+        ctx.wshape = params[0].shape if params else None
         return y[:, :N]
 
     @staticmethod
@@ -39,11 +44,14 @@ class LinearFn(torch.autograd.Function):
         dyf = torch.zeros(B, Np, dtype=torch.float32, device=dy.device)
         dyf[:, :N] = dy
         dx = torch.empty(B, K, dtype=torch.float32, device=dy.device)
+        # autograd mode: this call's own contribution goes to fresh tensors (a shared head is called three times per step)
+        gw = L.gw if ctx.nparams == 0 else torch.zeros_like(L.gw)
+        gb = L.gb if (ctx.nparams == 0 or L.gb is None) else torch.zeros_like(L.gb)
         if ctx.prec == BF16:
             dyb = torch.empty(B, Np, dtype=torch.bfloat16, device=dy.device)
             lib.cast_bf16(dyf, dyb)
             lib.gemm(dyb, L.w16, dx, B, K, N, b_mn=True)
-            lib.gemm(dyb, xb, L.gw, N, K, B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
+            lib.gemm(dyb, xb, gw, N, K, B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
         else:       # fp32-faithful: 3-piece splits along the reduction dimension of each product
             ds = torch.empty(B, 6 * Np, dtype=torch.bfloat16, device=dy.device)
             lib.split3(dyf, ds, 0)
@@ -52,11 +60,13 @@ class LinearFn(torch.autograd.Function):
             xr = torch.empty(6 * B, K, dtype=torch.bfloat16, device=dy.device)
             lib.split3(dyf, da, 2)
             lib.split3(ctx.x32, xr, 3)
-            lib.gemm(da, xr, L.gw, N, K, 6 * B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
+            lib.gemm(da, xr, gw, N, K, 6 * B, a_mn=True, b_mn=True, epilogue=lib.EPI_ATOMIC)
         names = {L.wname}
-        if L.gb is not None:
-            lib.colsum(dyf, L.gb, B, N)
+        if gb is not None:
+            lib.colsum(dyf, gb, B, N)
             names.add(L.bname)
+        if ctx.nparams:
+            return (None, None, None, dx, gw.view(ctx.wshape)) + ((gb,) if ctx.nparams > 1 else ())
         eng.arena.attach_grads(names)
         return None, None, None, dx
 
@@ -65,7 +75,8 @@ class BatchNormFn(torch.autograd.Function):
     """nn.BatchNorm1d in training mode on [B, F]; `bn` is the nn.BatchNorm1d module holding the buffers."""
 
     @staticmethod
-    def forward(ctx, eng, name, bn, x):
+    def forward(ctx, eng, name, bn, x, *params):
+        ctx.nparams = len(params)          # (weight, bias) in the autograd mode, see LinearFn
         a = eng.arena
         x = x.contiguous().float()
         B, F = x.shape
@@ -87,9 +98,14 @@ class BatchNormFn(torch.autograd.Function):
         B, F = x.shape
         dy = dy.contiguous().float()
         dx = torch.empty_like(x)
+        if ctx.nparams:
+            dg, db = torch.zeros(F, dtype=torch.float32, device=x.device), torch.zeros(F, dtype=torch.float32, device=x.device)
+        else:
+            dg, db = a.gview(name + ".weight"), a.gview(name + ".bias")
         lib.call("edb_bn1d_bwd", dy.data_ptr(), F, x.data_ptr(), F, B, F, a.view(name + ".weight").data_ptr(), mean.data_ptr(),
-                 invstd.data_ptr(), dx.data_ptr(), F, a.gview(name + ".weight").data_ptr(), a.gview(name + ".bias").data_ptr(),
-                 lib.stream_ptr())
+                 invstd.data_ptr(), dx.data_ptr(), F, dg.data_ptr(), db.data_ptr(), lib.stream_ptr())
+        if ctx.nparams:
+            return None, None, None, dx, dg, db
         a.attach_grads({name + ".weight", name + ".bias"})
         return None, None, None, dx
 
@@ -170,7 +186,7 @@ class TripletFn(torch.autograd.Function):
 
 def editor_loss(outputs, label, id_w=1.0, tri_w=1.0, eps=0.1):
     """engine/processor.py:82-92 over layers/make_loss.py:36-56 (softmax_triplet sampler, label smoothing on)."""
-    label = label.contiguous()
+    label = label.to(torch.int64).contiguous()
     total = outputs[-1].float().reshape(())
     for i in range(0, len(outputs) - 1, 2):
         total = total + id_w * CeSmoothFn.apply(outputs[i], label, eps).reshape(()) \

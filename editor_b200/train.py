@@ -55,12 +55,15 @@ class Trainer:
 
     def step(self, x, label, cam, writer=None, epoch=1):
         model = self.model
+        eng = model.engine()
+        eng.stats["grad_hook"] = self._on_grad_stage            # also tells the engine that the Trainer owns the exchange
+        if eng.arena is not None:
+            eng.arena.grad.zero_()          # the engine accumulates into live .grad views (torch semantics): zero per step
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outputs = model(x, label=label, cam_label=cam, view_label=None, img_path=None, writer=writer, epoch=epoch)
             loss = editor_loss(outputs, label)
         arena = model.engine().arena
         self._setup(arena)
-        model.engine().stats["grad_hook"] = self._on_grad_stage
         loss.backward()
         for w in self.pending:
             w.wait()

@@ -25,85 +25,7 @@ import yaml
 REF_ROOT = os.environ.get("EDITOR_REFERENCE_ROOT", "/root/reference")
 
 
-class _CfgNode(dict):
-    """Minimal yacs.config.CfgNode stand-in (attribute access, yaml merge, list merge)."""
-
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
-
-    def __setattr__(self, k, v):
-        self[k] = v
-
-    def clone(self):
-        out = _CfgNode()
-        for k, v in self.items():
-            out[k] = v.clone() if isinstance(v, _CfgNode) else (list(v) if isinstance(v, list) else v)
-        return out
-
-    def _merge(self, other):
-        for k, v in other.items():
-            if isinstance(v, dict):
-                if k not in self:
-                    self[k] = _CfgNode()
-                self[k]._merge(v)
-            else:
-                self[k] = v
-
-    def merge_from_file(self, path):
-        with open(path) as f:
-            self._merge(yaml.safe_load(f))
-
-    def merge_from_list(self, opts):
-        assert len(opts) % 2 == 0
-        for k, v in zip(opts[0::2], opts[1::2]):
-            node = self
-            parts = k.split(".")
-            for p in parts[:-1]:
-                node = node[p]
-            if isinstance(v, str):
-                try:
-                    v = yaml.safe_load(v)
-                except Exception:
-                    pass
-            node[parts[-1]] = v
-
-    def freeze(self):
-        pass
-
-    def defrost(self):
-        pass
-
-
-def _install_stubs():
-    if "yacs" not in sys.modules:
-        yacs = types.ModuleType("yacs")
-        yc = types.ModuleType("yacs.config")
-        yc.CfgNode = _CfgNode
-        yacs.config = yc
-        sys.modules["yacs"] = yacs
-        sys.modules["yacs.config"] = yc
-    if "pywt" not in sys.modules:
-        pywt = types.ModuleType("pywt")
-        s = 1.0 / math.sqrt(2.0)
-
-        class Wavelet:  # noqa: D401 - haar only
-            def __init__(self, name):
-                assert name in ("haar", "db1"), name
-                self.dec_lo = [s, s]
-                self.dec_hi = [-s, s]
-                self.rec_lo = [s, s]
-                self.rec_hi = [s, -s]
-
-        pywt.Wavelet = Wavelet
-        pywt.dwt_coeff_len = lambda N, L, mode="zero": (N + L - 1) // 2
-        sys.modules["pywt"] = pywt
-    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+from baseline.stubs import _CfgNode, install_stubs as _install_stubs  # noqa: E402,F401
 
 
 _PATCHED = {}

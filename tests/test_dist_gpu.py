@@ -1,0 +1,30 @@
+"""Multi-rank GPU correctness (needs >= 2 GPUs; skipped on a one-GPU box): see tests/dist_gpu_worker.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("al", ["1", "0"])
+def test_two_rank_allreduce_and_ddp_equal_trainer(al):
+    env = dict(os.environ, EDB_TEST_AL=al)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29%03d" % (os.getpid() % 1000),
+                          os.path.join(ROOT, "tests", "dist_gpu_worker.py")], capture_output=True, text=True, env=env,
+                         timeout=900)
+    assert out.returncode == 0, out.stderr[-4000:]
+    rep = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    print(json.dumps(rep))
+    for name, err in rep["bucket_rel_err"].items():
+        assert err < 1e-4, (name, err)               # fp32 atomics reorder sums; allreduce itself is exact per element order
+    assert rep["params_rank_spread"] == 0.0          # replicas stay bit-identical
+    assert rep["ddp_vs_trainer_param_err_rel_update"][0] < 5e-3, rep
+    assert abs(rep["ddp_loss"] - rep["trainer_loss"]) < 1e-3 * abs(rep["trainer_loss"])
+    assert rep["bn_running_mean_err"] < 1e-4

@@ -27,11 +27,9 @@ def timed(fn, flush, n=5):
     return tot / n
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--maps", default="bf16")
-    args = ap.parse_args()
+def run(batch=512, maps_dtype="bf16", sweep=((10, 2), (16, 1), (32, 2), (64, 4), (96, 8))):
+    """Returns the isolation report as a dict (bench.py embeds it as `sfts_isolation`)."""
+    args = argparse.Namespace(batch=batch, maps=maps_dtype)
     B, S, H, L = args.batch, 3 * args.batch, 12, 12
     dev = "cuda"
     peak = 6459.6
@@ -63,7 +61,7 @@ def main():
     st = lib.stream_ptr()
     esz = 2 if args.maps == "bf16" else 4
     out = {"batch": B, "maps_dtype": args.maps, "hbm_peak_gbs": peak, "runs": []}
-    for fk, hk in ((10, 2), (16, 1), (32, 2), (64, 4), (96, 8)):
+    for fk, hk in sweep:
         def f_freq():
             lib.call("edb_freq_counts", imgs[0].data_ptr(), imgs[1].data_ptr(), imgs[2].data_ptr(), B, 256, 128,
                      counts.data_ptr(), st)
@@ -89,12 +87,21 @@ def main():
         b_pack = 3 * B * 129 * 768 * 4 + 3 * B * (1 + n_sel) * 768 * 4
         tot_b, tot_t = b_freq + b_roll + b_pack, t_freq + t_roll + t_pack
         out["runs"].append({"frequency_keep": fk, "head_keep": hk, "kept_tokens_mean": n_sel,
+                            "bytes": {"freq_mask": b_freq, "rollout_topk": b_roll, "pack_bcc": b_pack},
                             "freq_mask": {"ms": t_freq, "GBps": b_freq / t_freq / 1e6, "frac": b_freq / t_freq / 1e6 / peak},
                             "rollout_topk": {"ms": t_roll, "GBps": b_roll / t_roll / 1e6, "frac": b_roll / t_roll / 1e6 / peak},
                             "pack_bcc": {"ms": t_pack, "GBps": b_pack / t_pack / 1e6, "frac": b_pack / t_pack / 1e6 / peak},
                             "sfts_total": {"ms": tot_t, "bytes": tot_b, "GBps": tot_b / tot_t / 1e6,
                                            "frac": tot_b / tot_t / 1e6 / peak}})
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--maps", default="bf16")
+    args = ap.parse_args()
+    print(json.dumps(run(args.batch, args.maps)))
 
 
 if __name__ == "__main__":
