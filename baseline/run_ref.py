@@ -2,7 +2,7 @@
 """Measured denominator of the north-star targets: the UNMODIFIED reference training loop on the GPU.
 
     python baseline/run_ref.py --model reference --amp fp16 ...   # the reference model, as engine/processor.py runs it
-    python baseline/run_ref.py --model reference --amp bf16 ...   # same loop, autocast dtype switched to bf16
+    python baseline/run_ref.py --model reference --amp bf16 ...   # same loop, `amp.autocast` of its namespace -> bf16
     python baseline/run_ref.py --model ours --amp fp16 ...        # THIS repo's make_model driven by that same loop
 
 Everything on the timed path is the reference's own code from the git-ignored copy ``baseline/_ref`` (made by
@@ -127,7 +127,12 @@ def run(args):
     torch.backends.cudnn.allow_tf32 = not args.no_tf32
     torch.backends.cuda.matmul.allow_tf32 = False          # torch default, what the reference runs with
     if args.amp == "bf16":
-        torch.set_autocast_dtype("cuda", torch.bfloat16)   # do_train's `amp.autocast(enabled=True)` then runs bf16
+        # do_train calls `amp.autocast(enabled=True)` (torch.cuda.amp: dtype defaults to float16 in its signature): give its
+        # namespace an `amp` whose autocast is bf16 -- the only way to run the UNMODIFIED loop under bf16 autocast
+        import types
+        processor.amp = types.SimpleNamespace(
+            GradScaler=torch.cuda.amp.GradScaler,
+            autocast=lambda enabled=True: torch.autocast("cuda", dtype=torch.bfloat16, enabled=enabled))
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -135,7 +140,7 @@ def run(args):
         loss_fn, center_criterion = make_loss(cfg, num_classes=C)
         model.load_state_dict(synth.synthetic_state_dict(seed=1111, num_class=C, camera_num=cams, al=al), strict=True)
         optimizer, optimizer_center = make_optimizer(cfg, model, center_criterion)
-    inst = 16 if args.batch % 16 == 0 else 2
+    inst = 16 if (args.batch % 16 == 0 and args.batch >= 32) else 2      # >= 2 identities: batch-hard triplet needs negatives
     batches = []
     for s in range(args.distinct_batches):
         x, label, cam = synth.synthetic_batch(args.batch, H, W, seed=1 + s, num_cams=cams, instances=inst)

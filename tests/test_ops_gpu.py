@@ -182,6 +182,33 @@ def test_attention_tensor_core_matches_cuda_core():
     assert _rel(grads[0].float(), grads[1].float()) < 3e-2
 
 
+@pytest.mark.parametrize("S", [1, 7, 64])
+def test_attention_tensor_core_vs_torch_autograd(S):
+    """attn_tc_fwd / attn_tc_bwd (the backbone's kernels) against torch autograd DIRECTLY (not through the CUDA-core kernel):
+    out, the stored P maps, and d_qkv.  S = 64 -> 768 (sequence, head) items: several per CTA once the kernels loop."""
+    from editor_b200 import lib
+    H = 12
+    qkv = (torch.randn(S * 129, 2304, generator=_g(3)) * 1.2).cuda().to(torch.bfloat16)
+    out = torch.zeros(S * 129, 768, dtype=torch.bfloat16, device="cuda")
+    P = torch.full((S * H, 129, 136), 7.0, dtype=torch.bfloat16, device="cuda")
+    lib.attention(qkv, out, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=0)
+    qr = qkv.float().requires_grad_(True)
+    ref, rmaps = _torch_attention(qr, [129] * S)
+    assert _rel(out.float(), ref.detach()) < 2e-2                    # tolerance: bf16 operands / bf16 P, fp32 accumulate
+    got = P.view(S, H, 129, 136)
+    assert _rel(got[..., :129].float(), torch.stack(rmaps).detach()) < 2e-2
+    assert torch.all(got[..., 129:] == 0)
+    d_out = torch.randn(S * 129, 768, generator=_g(4)).cuda().to(torch.bfloat16)
+    ref.backward(d_out.float())
+    d_qkv = torch.full_like(qkv, 3.0)
+    lib.attention(qkv, None, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=0, d_out=d_out, d_qkv=d_qkv,
+                  backward=True)
+    torch.cuda.synchronize()
+    err = ((d_qkv.float() - qr.grad).norm() / qr.grad.norm()).item()
+    print("attn_tc_bwd vs torch autograd: L2 rel %.3e, max rel %.3e" % (err, _rel(d_qkv.float(), qr.grad)))
+    assert err < 1e-2 and _rel(d_qkv.float(), qr.grad) < 3e-2        # tolerance: bf16 P / dS operands
+
+
 def test_selection_kernels_bit_exact():
     from editor_b200 import lib, synth
     for (H, W) in ((256, 128), (128, 256)):
