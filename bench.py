@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=8)
     ap.add_argument("--preheat", type=int, default=12, help="untimed conditioning steps before the warm-up")
     ap.add_argument("--gemm-mode", type=int, default=0, help="0 = CTA-pair tcgen05 tiles (default), 1 = single-CTA tiles")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step eagerly (no CUDA graph)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -369,12 +370,17 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # the whole step (forward + loss + backward + allreduce + SGD) as one CUDA graph: Trainer.capture; eager otherwise
+    graphed = (not args.no_graph) and (not fp32) and trainer.capture(xg, lg, cg)
+    if graphed:
+        xg, lg, cg = trainer.static_in       # device-resident inputs = the graph's static buffers (no per-step D2D copy)
+    step_fn = trainer.step_graphed if graphed else trainer.step
     # untimed conditioning before the W warm-up steps: the first second of load after an idle GPU runs into the power
     # limiter harder than the steady state does (first-region steps measured 15-30 % slower than later ones on some boxes)
     for _ in range(args.preheat):
-        trainer.step(xg, lg, cg)
+        step_fn(xg, lg, cg)
     for _ in range(args.warmup):
-        trainer.step(xg, lg, cg)
+        step_fn(xg, lg, cg)
     # long-lived objects (model, arena views, workspace) leave the cyclic collector's young generations: a full collection
     # landing inside the timed region cost one step ~18 ms (step_ms_each showed 57.9 ms once in eight)
     gc.collect()
@@ -388,7 +394,7 @@ def main():
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
     for i in range(args.steps):
-        loss, _ = trainer.step(xg, lg, cg)
+        loss, _ = step_fn(xg, lg, cg)
         marks[i].record()
     e1.record()
     barrier()
@@ -413,7 +419,7 @@ def main():
         xs, ls, cs = pf.get(i)
         if i + 1 < args.steps:
             pf.issue(i + 1)
-        loss, _ = trainer.step(xs, ls, cs)
+        loss, _ = step_fn(xs, ls, cs)       # graphed: one D2D copy into the graph's static inputs, then the replay
         pf.release(i)
         loss_pinned[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         loss_ev[i].record()
@@ -532,7 +538,8 @@ def main():
                        "parallelism": "dp%d" % world,
                        "l2_policy": "inputs+activations per step (>18 GB) far exceed the 126 MB L2",
                        "kept_tokens_mean": n_sel, "drop_path": drop_path, "preheat_steps": args.preheat,
-                       "step": "forward + CE/triplet loss + backward + grad allreduce + fused SGD"},
+                       "step": "forward + CE/triplet loss + backward + grad allreduce + fused SGD",
+                       "cuda_graph": bool(graphed), "cuda_graph_error": getattr(trainer, "capture_error", None)},
             "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,

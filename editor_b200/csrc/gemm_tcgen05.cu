@@ -20,7 +20,8 @@
 #include "abi_internal.h"
 
 #ifndef EDB_AUX_PREFETCH
-#define EDB_AUX_PREFETCH 1      // next tile's aux slab -> L2: 0 = off, 1 = cp.async.bulk.prefetch.L2 per row, 2 = prefetch.global.L2 lines
+#define EDB_AUX_PREFETCH 3      // next tile's aux slab -> L2: 0 = off, 1 = cp.async.bulk.prefetch.L2 per row, 2 = prefetch.global.L2
+//                                 lines, 3 = one cp.async.bulk.prefetch.tensor.2d per warp (32 x 64 box of a tensor map over aux)
 #endif
 // Experimental build switches for A/B runs on one box (make OUT=../lib_x EXTRA=-D...; EDB_LIB=.../lib_x/libeditor_b200.so
 // python tools/gemm_bench.py); both are OFF in the shipped library (measured together: fc1 forward 0.233 -> 0.230 ms, ~1 %):
@@ -68,6 +69,7 @@ struct GemmKernelParams {
     const int* M_dev;   // optional: number of valid rows read on the device (packed HMA rows; no host sync)
     const int* K_dev;   // optional: reduction length read on the device (wgrad over packed rows)
     float* colsum;      // optional (EPI_STORE / EPI_GELU_BWD): column sums of D accumulated with atomics (bias gradient)
+    int aux_tmap_ok;    // tmap_aux describes the bf16 aux matrix (EPI_GELU_BWD): slab prefetches go through it
 };
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -184,7 +186,7 @@ __device__ __forceinline__ void st4g(__nv_bfloat16* p, const float4& v, int nval
 template <int BN, int STAGES, int EPI, int NEPI, int CG>
 __global__ void __launch_bounds__(gemm_threads<NEPI>(), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmKernelParams p) {
+                 const __grid_constant__ CUtensorMap tmap_aux, const GemmKernelParams p) {
     using S = GemmSmem<BN, STAGES, CG>;
     constexpr int BNC = BN / CG;            // rows of B this CTA stages
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
@@ -432,9 +434,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (wn < num_work) {
                     int tm2, tn2, ks2;
                     decode(wn, tm2, tn2, ks2);
-                    const int r2 = (tm2 * CG + (int)rank) * BM + quarter * 32 + lane;
                     const int c2 = tn2 * BN + part * (BN / NPART);
                     constexpr int kSlabCols = BN / NPART;
+#if EDB_AUX_PREFETCH == 3
+                    // ONE tensor-map prefetch per warp for its whole 32-row x 64-column slab (the per-lane bulk prefetch
+                    // below compiles to a 32-iteration uniform-register loop: 14 % of this kernel's issued instructions,
+                    // profiles/r01 fc2-dgrad capture); rows / columns past the matrix are clipped by the tensor map
+                    if (kSlabCols == 64 && p.aux_tmap_ok && lane == 0)
+                        tma_prefetch_2d(&tmap_aux, c2, (tm2 * CG + (int)rank) * BM + quarter * 32);
+#else
+                    const int r2 = (tm2 * CG + (int)rank) * BM + quarter * 32 + lane;
                     const int esz = kAuxF32 ? 4 : 2;
                     if (pitch_ok && r2 < M_rt && c2 + kSlabCols <= p.N && (p.ld_aux * esz) % 16 == 0) {
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) + ((size_t)r2 * p.ld_aux + c2) * esz;
@@ -445,6 +454,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int b = 0; b < kSlabCols * esz; b += 128) prefetch_l2_line(src + b);
 #endif
                     }
+#endif
                 }
             }
             if (kAuxF32) {          // DropPath scale of each of this lane's rows: once per tile, not once per chunk
@@ -715,7 +725,8 @@ int num_sms() {
 }
 
 template <int BN, int STAGES, int EPI, int NEPI, int CG>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKernelParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tx, const GemmKernelParams& p,
+                       cudaStream_t stream) {
     using S = GemmSmem<BN, STAGES, CG>;
     static bool configured = false;
     if (!configured) {
@@ -728,7 +739,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
     const int units = num_sms() / CG;          // CTAs, or CTA pairs (one per TPC)
     const int grid = (num_work < units ? num_work : units) * CG;
     if (CG == 1) {
-        gemm_bf16_kernel<BN, STAGES, EPI, NEPI, CG><<<grid, gemm_threads<NEPI>(), S::kTotal, stream>>>(ta, tb, p);
+        gemm_bf16_kernel<BN, STAGES, EPI, NEPI, CG><<<grid, gemm_threads<NEPI>(), S::kTotal, stream>>>(ta, tb, tx, p);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid, 1, 1);
@@ -742,7 +753,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, EPI, NEPI, CG>, ta, tb, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, STAGES, EPI, NEPI, CG>, ta, tb, tx, p);
         if (e != cudaSuccess) return edb_set_error(EDB_ERR_CUDA, cudaGetErrorString(e));
     }
     cudaError_t e = cudaGetLastError();
@@ -799,11 +810,16 @@ int gemm_bf16(const EdbGemmDesc& g, cudaStream_t stream) {
     if (!g.b_mn_major) rc = make_tmap_bf16(&tb, g.B, g.K, g.N, g.ldb, BN / CG);
     else               rc = make_tmap_bf16(&tb, g.B, g.N, g.K, g.ldb, BK);
     if (rc != EDB_OK) return rc;
+    // bf16 aux (saved gelu'): a 64-column x 32-row box per epilogue warp, used for L2 prefetches of the next tile's slab
+    CUtensorMap tx = ta;
+    if (g.epilogue == EPI_GELU_BWD && (g.ld_aux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0 &&
+        make_tmap_bf16(&tx, g.aux, g.N, g.M, g.ld_aux, 32) == EDB_OK)
+        p.aux_tmap_ok = 1;
 #define EDB_LAUNCH_EPI(E, W)                                                          \
     case E:                                                                           \
-        if (CG == 2) return launch_gemm<256, 6, E, W, 2>(ta, tb, p, stream);           \
-        if (BN == 256) return launch_gemm<256, 4, E, W, 1>(ta, tb, p, stream);         \
-        return launch_gemm<128, 6, E, W, 1>(ta, tb, p, stream);
+        if (CG == 2) return launch_gemm<256, 6, E, W, 2>(ta, tb, tx, p, stream);       \
+        if (BN == 256) return launch_gemm<256, 4, E, W, 1>(ta, tb, tx, p, stream);     \
+        return launch_gemm<128, 6, E, W, 1>(ta, tb, tx, p, stream);
     switch (g.epilogue) {
         EDB_LAUNCH_EPI(EPI_STORE, 16)
         EDB_LAUNCH_EPI(EPI_GELU, EDB_GELU_EPI_WARPS)

@@ -137,6 +137,12 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// a whole tensor-map box into L2 (no shared-memory destination, no barrier): one instruction per box
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
 // one 128-byte line into L2 through the load/store unit (no TMA request)
 __device__ __forceinline__ void prefetch_l2_line(const void* gptr) {
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gptr) : "memory");

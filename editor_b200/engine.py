@@ -677,7 +677,10 @@ class EditorEngine:
         rates = self.model.BACKBONE.base.drop_path_rates
         if max(rates) <= 0.0:
             return None
-        keep = 1.0 - torch.tensor(rates, dtype=torch.float32, device=device).repeat_interleave(2).unsqueeze(1)  # [24,1]
+        keep = self.stats.get("droppath_keep")          # cached: a host->device copy is not allowed under graph capture
+        if keep is None or keep.device != device:
+            keep = 1.0 - torch.tensor(rates, dtype=torch.float32, device=device).repeat_interleave(2).unsqueeze(1)  # [24,1]
+            self.stats["droppath_keep"] = keep
         rnd = torch.rand((24, 3 * B), dtype=torch.float32, device=device)     # one draw for the whole step
         scales = torch.floor(keep + rnd) / keep                               # keep_prob + rand, floor, / keep_prob
         return list(scales.unbind(0))

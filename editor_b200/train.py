@@ -20,6 +20,7 @@ class Trainer:
         self.flags = None
         self.first = True
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.graph = None
 
     def _setup(self, arena):
         if self.mom is not None and self.mom.numel() == arena.total and self.mom.device == arena.flat.device:
@@ -75,3 +76,52 @@ class Trainer:
         arena._versions = [p._version for p in arena.params]   # the bf16 shadow was rewritten by the optimizer kernel
         self.first = False
         return loss, outputs
+
+    # ------------------------------------------------------------------ whole step as ONE CUDA graph
+    def capture(self, x, label, cam, warmup=3):
+        """Capture forward + loss + backward + bucketed allreduce + fused SGD into one CUDA graph (static input buffers):
+        ~700 kernel launches, the autograd bookkeeping and the ctypes calls of a step leave the critical path, the
+        launch gaps between the small tail / loss kernels close, and host jitter can no longer stall the GPU.  The bf16
+        step has no host synchronisation and no data-dependent launch configuration (packed row counts stay on the
+        device), which is what makes it capturable.  `warmup` eager steps run first on a side stream (workspace
+        allocation, first-step flags, NCCL communicator).  Returns False (and stays eager) if capture is impossible."""
+        model = self.model
+        if getattr(model, "precision", "auto") == "fp32":
+            return False                    # the fp32 parity mode reads row counts on the host
+        self.static_in = ({k: v.clone() for k, v in x.items()}, label.clone(), cam.clone())
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(*self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = lib.launch_count
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.static_loss, self.static_out = self.step(*self.static_in)
+        except Exception as e:          # noqa: BLE001 - any capture failure leaves the trainer in eager mode
+            self.graph, self.capture_error = None, repr(e)[:300]
+            torch.cuda.synchronize()
+            return False
+        self.graph = g
+        self.launches_per_replay = lib.launch_count - n0
+        return True
+
+    def step_graphed(self, x, label, cam):
+        """Replay the captured step on new inputs (device tensors; copied into the static buffers on the current stream)."""
+        if self.graph is None:
+            return self.step(x, label, cam)
+        sx, sl, sc = self.static_in
+        for k in sx:
+            if sx[k].data_ptr() != x[k].data_ptr():
+                sx[k].copy_(x[k], non_blocking=True)
+        if sl.data_ptr() != label.data_ptr():
+            sl.copy_(label, non_blocking=True)
+        if sc.data_ptr() != cam.data_ptr():
+            sc.copy_(cam, non_blocking=True)
+        self.graph.replay()
+        lib.launch_count += self.launches_per_replay
+        return self.static_loss, self.static_out

@@ -69,7 +69,9 @@ def _own_train(al, sd, x, label, cam, precision):
     model = ge._small_case(al, 4)[0].cuda().train()
     model.load_state_dict(sd, strict=True)
     model.precision = precision
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    # bf16 mode: forward AND loss under autocast, as engine/processor.py:79-92 runs them (and as ref16 above does);
+    # fp32 mode: no autocast anywhere, like ref32
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(precision != "fp32")):
         outs = model(x, label=label, cam_label=cam, writer=None, epoch=1)
         loss = orc.reference_loss([o.float() for o in outs], label)
     loss.backward()
@@ -118,6 +120,7 @@ def test_bf16_error_is_within_the_references_own_bf16_spread(al):
     assert rep["selection_bits_differing_from_ref32"]["own32"] == 0           # index: bit-exact (fp32 mode)
     assert max(rep["outputs_rel_err_vs_ref32"]["own32"]) < 1e-3               # tolerance: 1e-3 rel, fp32 (north_star)
     assert abs(lw32 - l32) < 1e-3 * abs(l32)
+    assert rep["grad_rel_err_vs_ref32"]["own32"]["median"] < 2e-3 and rep["grad_rel_err_vs_ref32"]["own32"]["max"] < 2e-2, rep
     same_sel = rep["selection_bits_differing_from_ref32"]["own16"] == 0 and rep["selection_bits_differing_from_ref32"]["ref16"] == 0
     if same_sel:
         for e_own, e_ref in zip(rep["outputs_rel_err_vs_ref32"]["own16"], rep["outputs_rel_err_vs_ref32"]["ref16"]):
@@ -170,4 +173,6 @@ def test_full_size_eval_matches_reference_on_gpu(al):
     assert rep["feature_rel_err_vs_ref32"]["own32"] < 1e-3                    # tolerance: 1e-3 rel fp32
     e_own, e_ref = rep["feature_rel_err_vs_ref32"]["own16_on_agreeing"], rep["feature_rel_err_vs_ref32"]["ref16_on_agreeing"]
     assert e_own <= max(1e-2, 1.25 * e_ref), rep                               # tolerance: 1e-2 bf16, or the reference's own spread
-    assert rep["samples_with_selection_differing_from_ref32"]["own16"] <= max(8, 2 * rep["samples_with_selection_differing_from_ref32"]["ref16"])
+    # bf16 rollout scores collide at 8 mantissa bits (SURVEY.md hard part 1-iii): index equality with fp32 is statistical in
+    # bf16 for the reference too -- ours must not flip more samples than the reference's own bf16 autocast run does
+    assert rep["samples_with_selection_differing_from_ref32"]["own16"] <= max(8, rep["samples_with_selection_differing_from_ref32"]["ref16"])

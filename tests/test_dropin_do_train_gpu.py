@@ -151,3 +151,40 @@ def test_gradscaler_torch_sgd_equals_fused_trainer():
     for k in ("FUSE_BN.running_mean", "FUSE_block.memory_cls.RGB_centers"):
         a, b = m1.state_dict()[k], m2.state_dict()[k]
         assert ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item() < 1e-3
+
+
+def test_graphed_step_equals_eager_step():
+    """Trainer.capture: the whole training step replayed as one CUDA graph == the same steps launched eagerly (parameters,
+    BatchNorm statistics, OCFR centres after 3 steps on changing batches; DROP_PATH 0 so that no RNG stream is involved)."""
+    def fresh(seed):
+        model, sd, x, label, cam, _ = ge._small_case(False, 4, seed=seed)
+        return model.cuda().train(), sd, {k: v.cuda() for k, v in x.items()}, label.cuda(), cam.cuda()
+
+    batches = [fresh(s)[2:] for s in (1, 2, 3)]
+    m1, sd0, *_ = fresh(1)
+    t1 = Trainer(m1)
+    for b in batches:
+        l1, _ = t1.step(*b)
+    m2, _, x, label, cam = fresh(1)
+    t2 = Trainer(m2)
+    assert t2.capture(x, label, cam, warmup=2), getattr(t2, "capture_error", None)
+    m2.load_state_dict(sd0, strict=True)            # undo the warm-up / capture steps: same start as m1
+    t2.mom.zero_()
+    t2.first = True                                   # (captured with first=False: momentum buffer is zero, same arithmetic)
+    m2.engine().arena.refresh16(force=True)
+    for b in batches:
+        l2, _ = t2.step_graphed(*b)
+    torch.cuda.synchronize()
+    assert abs(l1.item() - l2.item()) < 1e-3 * abs(l1.item())
+    p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    worst = (0.0, None)
+    for k in p1:
+        upd = (p1[k].detach().cpu() - sd0[k]).norm().item()
+        if p1[k].grad is None or upd < 1e-9:
+            continue
+        worst = max(worst, ((p1[k].detach() - p2[k].detach()).norm().item() / upd, k))
+    print("graphed vs eager, largest parameter difference relative to the 3-step update:", worst)
+    assert worst[0] < 5e-3, worst
+    for k in ("FUSE_BN.running_var", "BACKBONE_BN.running_mean", "FUSE_block.memory_cls.TIR_centers"):
+        a, b = m1.state_dict()[k], m2.state_dict()[k]
+        assert ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item() < 1e-3, k

@@ -113,7 +113,9 @@ def test_state_dict_schema_and_config_surface():
 def test_full_size_eval_matches_reference_golden(al):
     """B = 128 (BASELINE.json size) against the committed golden of the UNMODIFIED reference (tests/golden/make_golden_b128.py,
     CPU fp32, CUDA top-k tie rule): fp32-faithful mode -> selection index bit-exact on all 128 samples, features 1e-3;
-    bf16 mode -> selection mismatch count reported (<= 8 samples), features 1e-2-class on the samples whose selection agrees."""
+    bf16 mode -> selection mismatch count reported, features 1e-2-class on the samples whose selection agrees.  (Measured on
+    B200, profiles/r02_bf16_spread_b128_*.json: the REFERENCE under bf16 autocast selects a different token set than its own
+    fp32 run on 105-107 of these 128 samples -- bf16 rollout scores tie at 8 mantissa bits -- this path on 38-49.)"""
     from editor_b200 import synth
     name = "rgbnt201" if al else "rgbnt100"
     path = os.path.join(HERE, "golden", "ref_b128_%s.pt" % name)
@@ -133,9 +135,9 @@ def test_full_size_eval_matches_reference_golden(al):
     err = _rel(out16[~diff], g["eval_cls4t"][~diff])
     print("bf16 eval at B=128: %d of 128 samples select a different token set than fp32; feature rel err on the rest %.3e"
           % (int(diff.sum()), err))
-    assert int(diff.sum()) <= 8
-    assert err < 2e-2      # tolerance: bf16 operands through 12 + 2 blocks; the reference's own bf16 autocast spread is
-    #                        measured next to it in tests/test_bf16_spread_gpu.py
+    assert int(diff.sum()) <= 64        # statistical, not bitwise, in bf16 (see the docstring); fp32 above is bit-exact
+    assert err < 1e-2      # tolerance: 1e-2 bf16 (north_star); measured 5.1e-3 / 6.3e-3, the reference's own bf16 autocast
+    #                        spread on the same samples is 7.0e-3 / 8.0e-3 (tests/test_bf16_spread_gpu.py)
 
 
 def test_full_size_batch_properties():
