@@ -21,6 +21,9 @@ P_LD = 136                      # pitch of the stored attention maps (129 padded
 MAX_SEL = 82                    # <= 24 per modality x 3 + FREQUENCY_KEEP 10 with the default config
 SCALE = 64 ** -0.5
 BF16, FP32 = "bf16", "fp32"
+# the backward reports a finished slice of the gradient arena after these backbone blocks (bucketed allreduce, train.py):
+# every two blocks, so that the last bucket ("rest" = blocks 1-0 + embeddings, 60 MB) is all that cannot overlap
+GRAD_STAGE_BLOCKS = (10, 8, 6, 4, 2)
 
 
 def _align(n, a=64):
@@ -115,6 +118,7 @@ class Arena:
         self._ptrs = [p.data_ptr() for p in self.params]
         self._versions = None
         self.generation = 0          # bumped by the fused optimizer kernel (it updates parameters without torch knowing)
+        self.carry, self.carry_live = None, False
 
     def view(self, name):
         o, n, shape = self.offsets[name]
@@ -142,22 +146,38 @@ class Arena:
 
     def prepare_grads(self):
         """Called at the start of every training forward.  torch semantics: ``.grad`` ACCUMULATES until the caller zeroes
-        it (engine/processor.py:72 ``optimizer.zero_grad()``; gradient accumulation over micro-batches must keep working).
+        it (engine/processor.py:72 ``optimizer.zero_grad()``; gradient accumulation over micro-batches must keep working),
+        while the kernels of one backward WRITE most gradients (bias / LayerNorm column sums) and only accumulate the
+        split-K weight gradients -- they need a zeroed arena per backward.
         * every ``p.grad`` is None (``zero_grad(set_to_none=True)``, the torch default) -> one memset of the arena;
-        * ``p.grad`` is already the arena view -> left alone: the kernels accumulate on top (whoever zeroed the views in
-          place -- ``zero_grad(set_to_none=False)`` -- zeroed the arena);
-        * ``p.grad`` is a foreign tensor (assigned by the caller) -> its value is adopted into the arena once, here, and
-          ``p.grad`` re-pointed at the view, so the backward never has to add into it piecewise."""
+        * some ``p.grad`` is live (accumulation, or ``zero_grad(set_to_none=False)``) -> what the caller holds is saved to
+          a second flat buffer (``carry``), the arena is zeroed, and ``finish_grads`` -- called by the last backward node
+          of the step -- adds the carry back: ``p.grad`` ends up as old + new, as with torch's AccumulateGrad.  Foreign
+          ``.grad`` tensors (assigned by the caller) are adopted into the carry once and re-pointed at the arena view."""
+        self.carry_live = False
         if not any(p.grad is not None for p in self.params):
             self.grad.zero_()
             return
+        if self.carry is None:
+            self.carry = torch.empty_like(self.grad)
+        # live arena views carry their old value through one flat copy; parameters without a .grad carry nothing, foreign
+        # tensors carry their own value
+        self.carry.copy_(self.grad)
         for name, p in zip(self.names, self.params):
-            gv = self.gview(name)
+            o, n, shape = self.offsets[name]
             if p.grad is None:
-                gv.zero_()
-            elif p.grad.data_ptr() != gv.data_ptr():
-                gv.copy_(p.grad)
-                p.grad = gv
+                self.carry[o:o + n].zero_()
+            elif p.grad.data_ptr() != self.grad[o:o + n].data_ptr():
+                self.carry[o:o + n].view(shape).copy_(p.grad)
+                p.grad = self.grad[o:o + n].view(shape)
+        self.grad.zero_()
+        self.carry_live = True
+
+    def finish_grads(self):
+        """End of the step's backward (the backbone node runs last): old + new for callers that accumulate."""
+        if self.carry_live:
+            self.grad.add_(self.carry)
+            self.carry_live = False
 
     def attach_grads(self, names=None):
         """Expose the gradient arena through ``p.grad`` (what GradScaler / torch optimizers of the unchanged caller
@@ -300,7 +320,7 @@ class EditorEngine:
         self._dgrad32(g, bp.proj, datt, rows)
         self._wgrad32(g, sv["att"], bp.proj, rows)
         dqkv = ws.get("dqkv32", (cap, 3 * DIM), torch.float32)
-        attn_bwd(sv["qkv"], sv["P"], datt, dqkv)
+        attn_bwd(sv["qkv"], sv["P"], datt, dqkv, sv["att"])
         if bp.qkv.gb is not None:
             lib.colsum(dqkv, bp.qkv.gb, rows, 3 * DIM)
         self._dgrad32(dqkv, bp.qkv, dln, rows)
@@ -360,7 +380,7 @@ class EditorEngine:
         lib.gemm(gb, bp.proj.w16, datt, rows, DIM, DIM, b_mn=True, M_dev=rd,
                  colsum=bp.qkv.gb[2 * DIM:] if bp.qkv.gb is not None else None)
         self._wgrad(gb, sv["att"], bp.proj, rows, rd)
-        attn_bwd(sv["qkv"], sv["P"], datt, dqkv)
+        attn_bwd(sv["qkv"], sv["P"], datt, dqkv, sv["att"])
         if bp.qkv.gb is not None:
             lib.colsum(dqkv, bp.qkv.gb, rows, DIM)
         lib.gemm(dqkv, bp.qkv.w16, dln, rows, DIM, 3 * DIM, b_mn=True, M_dev=rd)
@@ -435,8 +455,9 @@ class EditorEngine:
                           self.bb_norm.gg, self.bb_norm.gb, last.fc2.gb, R,
                           row_scale=None if dp is None else dp[23], scale_group=NTOK)
 
-        def attn_bwd(qkv, P, datt, dqkv):
-            lib.attention(qkv, None, P, S, HEADS, NTOK, SCALE, fixed_len=NTOK, p_rows=NTOK, ldp=P_LD,
+        def attn_bwd(qkv, P, datt, dqkv, att):
+            # att = the forward output O: the tensor-core backward takes delta_i = dO_i . O_i from it
+            lib.attention(qkv, att, P, S, HEADS, NTOK, SCALE, fixed_len=NTOK, p_rows=NTOK, ldp=P_LD,
                           impl=self.stats.get("attn_impl", 0), d_out=datt, d_qkv=dqkv, backward=True)
         for l in range(11, -1, -1):
             bp = self.bb_blocks[l]
@@ -444,7 +465,7 @@ class EditorEngine:
             rs_a = None if dp is None else dp[2 * l]
             rs_prev = None if (dp is None or l == 0) else dp[2 * l - 1]
             self._block_bwd(g, gb, R, bp, sv["blocks"][l], attn_bwd, prev_gb, rs_a, rs_prev, NTOK)
-            if l in (8, 4):
+            if l in GRAD_STAGE_BLOCKS:
                 self._grad_stage("blocks_from_%d" % l)
         base = "BACKBONE.base."
         dpatch = ws.get("dpatch", (S * NPATCH, DIM), torch.bfloat16)
@@ -467,13 +488,13 @@ class EditorEngine:
         lib.layernorm_bwd(d_tokens.reshape(R, DIM), sv["x_last"], sv["mf"], sv["rf"], self.bb_norm.g, None, g, None,
                           self.bb_norm.gg, self.bb_norm.gb, self.bb_blocks[-1].fc2.gb, R)
 
-        def attn_bwd(qkv, P, datt, dqkv):
+        def attn_bwd(qkv, P, datt, dqkv, att):
             lib.attention(qkv, None, P, S, HEADS, NTOK, SCALE, fixed_len=NTOK, p_rows=NTOK, ldp=P_LD, impl=1, d_out=datt,
                           d_qkv=dqkv, backward=True)
         for l in range(11, -1, -1):
             prev_gb = self.bb_blocks[l - 1].fc2.gb if l > 0 else None
             self._block_bwd32(g, R, self.bb_blocks[l], sv["blocks"][l], attn_bwd, prev_gb)
-            if l in (8, 4):
+            if l in GRAD_STAGE_BLOCKS:
                 self._grad_stage("blocks_from_%d" % l)
         base = "BACKBONE.base."
         dpatch = ws.get("dpatch32", (S * NPATCH, DIM), torch.float32)
@@ -542,7 +563,7 @@ class EditorEngine:
                           total_rows=total_rows)
             return Pm
 
-        def bwd(qkv, P, datt, dqkv):
+        def bwd(qkv, P, datt, dqkv, att):
             lib.attention(qkv, None, P, nseq, HEADS, max_len, SCALE, seq_off=seq_off, p_rows=p_rows, ldp=ldp, impl=impl,
                           d_out=datt, d_qkv=dqkv, backward=True, total_rows=total_rows)
         return fwd, bwd
@@ -629,6 +650,16 @@ class EditorEngine:
         if p == "auto":
             return BF16 if (training or torch.is_autocast_enabled("cuda")) else FP32
         return p
+
+    def _warn_pending(self):
+        """The gradient arena holds ONE backward at a time: fwd/bwd, fwd/bwd accumulates correctly; fwd, fwd, bwd, bwd does
+        not (the second forward re-zeroes the arena the first backward is going to write).  A training forward that is
+        never back-propagated is harmless, so this only warns, once."""
+        if self.stats.get("pending_backward") and not self.stats.get("warned_pending"):
+            import warnings
+            warnings.warn("editor_b200: a training forward started before the backward of the previous one ran; gradients "
+                          "of overlapping forward passes are not supported (run fwd/bwd, fwd/bwd)")
+            self.stats["warned_pending"] = True
 
     def _check_cam(self, cam, B, training):
         """`sie_embed[cam[b]]` is gathered by the embed kernel: range-check on the device (no host sync) on the first
@@ -717,13 +748,14 @@ class EditorEngine:
         if ag:
             # autograd / DistributedDataParallel mode: the arena is scratch for ONE forward+backward, parameter gradients
             # leave through the autograd graph (AccumulateGrad -> DDP reducer hooks), p.grad is torch's business
-            if self.stats.get("pending_backward"):
-                raise lib.EdbError("autograd (DDP) mode supports one backward per forward: a second training forward was "
-                                   "started before the backward of the previous one")
-            self.stats["pending_backward"] = True
+            self._warn_pending()
             self.arena.grad.zero_()
+        elif self.stats.get("trainer_owns_grads"):
+            pass                            # editor_b200.train.Trainer zeroes the arena itself, once per step
         else:
+            self._warn_pending()
             self.arena.prepare_grads()
+        self.stats["pending_backward"] = True
         P = (lambda *names: tuple(self.arena.params[self.arena.names.index(n)] for n in names)) if ag else (lambda *n: ())
         label = self._check_labels(label, B, rgb.device, check)
         dp = self._droppath(B, rgb.device)
@@ -803,6 +835,7 @@ class _BackboneFn(torch.autograd.Function):
         eng.backbone_backward(ctx.sv, d_tokens)
         eng._mark("bb_bwd_end")
         eng.stats["pending_backward"] = False
+        eng.arena.finish_grads()
         if ctx.ag:      # clones: AccumulateGrad may keep the tensor it is handed as p.grad, the arena is reused next step
             return (None,) * 8 + tuple(eng.arena.gview(n).clone() for n in eng.bb_names)
         eng.arena.attach_grads(set(eng.bb_names))

@@ -146,10 +146,21 @@ gemm_timing = None  # bench.py sets this to a list to collect one record (shape,
 #                     events) per GEMM launch; FLOPs / bytes are computed from the ACTUAL row counts after the step
 
 
+_capture_debug = os.environ.get("EDB_CAPTURE_DEBUG")       # tools/graph_probe.py: report the call that invalidates a capture
+_capture_was_active = False
+
+
 def call(name, *args):
-    global launch_count
+    global launch_count, _capture_was_active
     launch_count += 1
     check(getattr(load(), name)(*args))
+    if _capture_debug:
+        active = torch.cuda.is_current_stream_capturing()
+        if _capture_was_active and not active:
+            import traceback
+            print("EDB_CAPTURE_DEBUG: capture no longer active after %s (launch %d)" % (name, launch_count), flush=True)
+            traceback.print_stack(limit=8)
+        _capture_was_active = active
 
 
 def gemm_set_mode(mode):

@@ -5,6 +5,7 @@ import torch
 import torch.distributed as dist
 
 from . import lib
+from .engine import GRAD_STAGE_BLOCKS
 
 
 from .tail import editor_loss  # noqa: E402,F401  (CUDA kernels: label-smoothed CE + batch-hard soft-margin triplet)
@@ -39,10 +40,14 @@ class Trainer:
         # gradient buckets = contiguous arena slices in the order the backward completes them (the arena follows
         # named_parameters(): backbone embeddings, blocks 0..11, norm, fc, then FUSE_block and the heads)
         off = lambda n: arena.offsets[n][0]                                    # noqa: E731
-        b8, b4 = off("BACKBONE.base.blocks.8.norm1.weight"), off("BACKBONE.base.blocks.4.norm1.weight")
         after = off("FUSE_block.normR.weight")
-        self.buckets = {"after_backbone": (after, arena.total), "blocks_from_8": (b8, after), "blocks_from_4": (b4, b8),
-                        "rest": (0, b4)}
+        self.buckets = {"after_backbone": (after, arena.total)}
+        hi = after
+        for l in GRAD_STAGE_BLOCKS:                                            # descending block indices
+            lo = off("BACKBONE.base.blocks.%d.norm1.weight" % l)
+            self.buckets["blocks_from_%d" % l] = (lo, hi)
+            hi = lo
+        self.buckets["rest"] = (0, hi)
         self.pending = []
 
     def _on_grad_stage(self, stage):
@@ -58,8 +63,10 @@ class Trainer:
         model = self.model
         eng = model.engine()
         eng.stats["grad_hook"] = self._on_grad_stage            # also tells the engine that the Trainer owns the exchange
+        eng.stats["trainer_owns_grads"] = True                  # ... and the gradient arena: zeroed here, once per step
+        eng.stats["pending_backward"] = False
         if eng.arena is not None:
-            eng.arena.grad.zero_()          # the engine accumulates into live .grad views (torch semantics): zero per step
+            eng.arena.grad.zero_()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outputs = model(x, label=label, cam_label=cam, view_label=None, img_path=None, writer=writer, epoch=epoch)
             loss = editor_loss(outputs, label)

@@ -144,7 +144,8 @@ int edb_gelu_bwd_f32(const float* dh, const float* pre, float* out, size_t n, vo
  * Also serves AttentionMask (vit_pytorch.py:240-258) on packed kept tokens. */
 typedef struct EdbAttnDesc {
     const void* qkv; long long ld_qkv;
-    void* out; long long ld_out;
+    void* out; long long ld_out;            /* forward: O.  backward: the SAME forward output, read-only -- required by the
+                                               tensor-core 129-token path (delta_i = dO_i . O_i), ignored by the others */
     void* P; long long p_rows; long long ldp;
     const int* seq_off; int fixed_len; int nseq; int heads; int max_len;
     float scale;

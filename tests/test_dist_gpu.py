@@ -25,6 +25,7 @@ def test_two_rank_allreduce_and_ddp_equal_trainer(al):
     for name, err in rep["bucket_rel_err"].items():
         assert err < 1e-4, (name, err)               # fp32 atomics reorder sums; allreduce itself is exact per element order
     assert rep["params_rank_spread"] == 0.0          # replicas stay bit-identical
-    assert rep["ddp_vs_trainer_param_err_rel_update"][0] < 5e-3, rep
+    agree = rep["ddp_vs_trainer_param_err_rel_update"]
+    assert agree["whole_model"] < 2e-3 and agree["per_tensor_median"] < 5e-3, rep
     assert abs(rep["ddp_loss"] - rep["trainer_loss"]) < 1e-3 * abs(rep["trainer_loss"])
     assert rep["bn_running_mean_err"] < 1e-4

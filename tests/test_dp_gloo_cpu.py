@@ -101,8 +101,16 @@ def test_trainer_flags_and_gradient_buckets():
     off = lambda n: arena.offsets[n][0]                                        # noqa: E731
     lo, hi = t.buckets["after_backbone"]
     assert all(lo <= off(n) < hi for n in arena.names if not n.startswith("BACKBONE.base."))
-    lo, hi = t.buckets["blocks_from_8"]
-    assert all(lo <= off(n) < hi for n in arena.names if any(n.startswith("BACKBONE.base.blocks.%d." % i) for i in (8, 9, 10, 11)))
+    from editor_b200.engine import GRAD_STAGE_BLOCKS
+    assert list(t.buckets) == ["after_backbone"] + ["blocks_from_%d" % l for l in GRAD_STAGE_BLOCKS] + ["rest"]
+    top = 12
+    for l in GRAD_STAGE_BLOCKS:              # bucket "blocks_from_l" = blocks l .. (previous stage - 1); the first one also
+        lo, hi = t.buckets["blocks_from_%d" % l]                               # holds the final norm and the unused fc
+        assert all(lo <= off(n) < hi for n in arena.names
+                   if any(n.startswith("BACKBONE.base.blocks.%d." % i) for i in range(l, top)))
+        top = l
+    lo, hi = t.buckets["blocks_from_%d" % GRAD_STAGE_BLOCKS[0]]
+    assert lo <= off("BACKBONE.base.norm.weight") < hi
     lo, hi = t.buckets["rest"]
     assert all(lo <= off(n) < hi for n in ("BACKBONE.base.cls_token", "BACKBONE.base.pos_embed",
                                            "BACKBONE.base.patch_embed.proj.weight", "BACKBONE.base.blocks.0.mlp.fc2.bias"))

@@ -175,8 +175,8 @@ def test_attention_tensor_core_matches_cuda_core():
     grads = []
     for impl in (0, 1):
         d_qkv = torch.zeros_like(qkv)
-        lib.attention(qkv, None, maps[1], S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=impl, d_out=d_out,
-                      d_qkv=d_qkv, backward=True)
+        lib.attention(qkv, outs[1] if impl == 0 else None, maps[1], S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136,
+                      impl=impl, d_out=d_out, d_qkv=d_qkv, backward=True)
         grads.append(d_qkv)
     torch.cuda.synchronize()
     assert _rel(grads[0].float(), grads[1].float()) < 3e-2
@@ -201,7 +201,7 @@ def test_attention_tensor_core_vs_torch_autograd(S):
     d_out = torch.randn(S * 129, 768, generator=_g(4)).cuda().to(torch.bfloat16)
     ref.backward(d_out.float())
     d_qkv = torch.full_like(qkv, 3.0)
-    lib.attention(qkv, None, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=0, d_out=d_out, d_qkv=d_qkv,
+    lib.attention(qkv, out, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, impl=0, d_out=d_out, d_qkv=d_qkv,
                   backward=True)
     torch.cuda.synchronize()
     err = ((d_qkv.float() - qr.grad).norm() / qr.grad.norm()).item()

@@ -26,7 +26,7 @@ def t(fn, n=10):
 
 
 fwd = t(lambda: lib.attention(qkv, out, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136))
-bwd = t(lambda: lib.attention(qkv, None, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, d_out=d_out, d_qkv=d_qkv, backward=True))
+bwd = t(lambda: lib.attention(qkv, out, P, S, H, 129, 0.125, fixed_len=129, p_rows=129, ldp=136, d_out=d_out, d_qkv=d_qkv, backward=True))
 fb = (228 + 161 + 76) * 1.0
 bb = (228 + 161 + 76 + 228) * 1.0
 print("attn_tc fwd %.3f ms (%.0f GB/s algorithmic)   bwd %.3f ms (%.0f GB/s)" % (fwd, fb / fwd, bwd, bb / bwd))
