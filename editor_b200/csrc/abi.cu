@@ -170,4 +170,12 @@ int edb_eval_rank(const float* dist, long long ldd, int q, int g, const long lon
                   const long long* q_key, const long long* g_key, double* ap, int* first_rank, int* overflow, void* stream) {
     return edb::eval_rank(dist, ldd, q, g, q_pid, g_pid, q_key, g_key, ap, first_rank, overflow, ST);
 }
+size_t edb_augment_workspace_bytes(int B, int Hs, int Ws, int W) { return edb::augment_workspace_bytes(B, Hs, Ws, W); }
+int edb_augment_u8(const unsigned char* src_rgb, const unsigned char* src_ni, const unsigned char* src_ti, int B, int Hs,
+                   int Ws, int H, int W, int pad, const int* hb, const int* hk, int ksh, const int* vb, const int* vk,
+                   int ksv, const float* mean, const float* std, const EdbAugImage* params, const float* noise,
+                   float* out_rgb, float* out_ni, float* out_ti, void* workspace, size_t ws_bytes, void* stream) {
+    return edb::augment_u8(src_rgb, src_ni, src_ti, B, Hs, Ws, H, W, pad, hb, hk, ksh, vb, vk, ksv, mean, std, params, noise,
+                           out_rgb, out_ni, out_ti, workspace, ws_bytes, ST);
+}
 }  // extern "C"

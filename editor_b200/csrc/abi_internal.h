@@ -94,4 +94,10 @@ int eval_distmat(const float* qf, long long ldq, int Q, const float* gf, long lo
 int eval_rank(const float* dist, long long ldd, int Q, int G, const long long* q_pid, const long long* g_pid,
               const long long* q_key, const long long* g_key, double* ap, int* first_rank, int* overflow, cudaStream_t st);
 
+size_t augment_workspace_bytes(int B, int Hs, int Ws, int W);
+int augment_u8(const uint8_t* s0, const uint8_t* s1, const uint8_t* s2, int B, int Hs, int Ws, int H, int W, int pad,
+               const int* hb, const int* hk, int ksh, const int* vb, const int* vk, int ksv, const float* mean,
+               const float* stdv, const EdbAugImage* params, const float* noise, float* o0, float* o1, float* o2,
+               void* workspace, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace edb

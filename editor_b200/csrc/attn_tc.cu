@@ -366,7 +366,6 @@ constexpr uint32_t BT_TOTAL = BT_BAR + 128;
 constexpr uint32_t BT_TM_DP = 0, BT_TM_DV = 128, BT_TM_DQ = 0, BT_TM_DK = 64;
 
 struct AttnTcBwdParams {
-    const __nv_bfloat16* out; long long ld_out;     // forward output O (delta_i = dO_i . O_i)
     const __nv_bfloat16* qkv; long long ld_qkv;
     __nv_bfloat16* d_qkv;
     const __nv_bfloat16* P;
@@ -379,15 +378,14 @@ struct AttnTcBwdParams {
 // a 128-byte row of a swizzled smem tile (the contribution of the key / query that is not on the MMA tile)
 __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr, float a = 0.f, const uint8_t* tile = nullptr,
                                                  int line = 0) {
-    // both halves of the row are requested before the one wait (the kernel is persistent: its loop body stays in the
-    // instruction cache, so the unrolled form no longer costs instruction fetches)
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32(taddr, r0);
-    tmem_ld_32x32(taddr + 32, r1);
-    tmem_ld_wait();
-#pragma unroll
+    // rolled on purpose (here and in the two dS passes below): the backward kernel is executed once per CTA, straight
+    // through; fully unrolled it was 150 KB of SASS -- more than the instruction cache -- and 17 % of its stall samples
+    // were instruction fetches
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-        const uint32_t* r = c == 0 ? r0 : r1;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
 #pragma unroll
         for (int t = 0; t < 32; t += 8) {
             float v[8];
@@ -710,66 +708,50 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_q128, const __grid_co
             const int s = blk / p.H, h = blk - s * p.H, row0 = s * AT_L;
             const __nv_bfloat16* Pg = p.P + (size_t)blk * AT_L * AT_PLD;
             const float p128 = __bfloat162float(Pg[(size_t)(i + 1) * AT_PLD + 128]);     // P[token i+1][key 128]
-            // delta_i = sum_j dP_ij P_ij = dO_i . O_i  (O = P V; the FlashAttention identity): one 64-long dot product with the
-            // saved forward output instead of a pass over the 129 dP / P columns -- and no dependence on the dP MMA
-            uint4 orow[8];
-            {
-                const uint4* og = reinterpret_cast<const uint4*>(p.out + (size_t)(row0 + 1 + i) * p.ld_out + h * AT_HD);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) orow[c] = og[c];
-            }
             mbar_wait(bar_vdo, ph);
             const float dp128 = dot_rows64(sdO, i, sV, 128);                              // dP[i][128] = dO_i . V_128
-            float delta = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 ud = *reinterpret_cast<const uint4*>(sdO + sw128(i, c));
-                const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
-                const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&orow[c]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float2 fd = __bfloat1622float2(hd[t]), fo = __bfloat1622float2(ho[t]);
-                    delta += fd.x * fo.x + fd.y * fo.y;
-                }
-            }
             mbar_arrive(bar_early);                  // done with V and dO
-            const float ds128 = __bfloat162float(__float2bfloat16(p128 * (dp128 - delta) * p.scale));
-            dscol[i] = ds128;
             mbar_wait(bar_qkp, ph);
             mbar_wait(bar_dp, ph);
-            mbar_wait(bar_dv, ph);                   // P is no longer read by the dV MMA: overwrite it with dS
             tc_fence_after();
-            {
-                // dS = P o (dP - delta) * scale, 32 score columns per chunk; the TMEM load of chunk c+1 is in flight while
-                // chunk c is processed
-                uint32_t ra[32], rb[32];
-                auto ds_chunk = [&](int c, const uint32_t* r) {
+            float delta = p128 * dp128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {            // 32 score columns per pass
+                uint32_t r[32];
+                tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4* pa = reinterpret_cast<uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
-                        uint4 u = *pa;
-                        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float2 f = __bfloat1622float2(hh[t]);
-                            hh[t] = __floats2bfloat162_rn(f.x * (__uint_as_float(r[q * 8 + 2 * t]) - delta) * p.scale,
-                                                          f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale);
-                        }
-                        *pa = u;
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = __bfloat1622float2(hh[t]);
+                        delta += f.x * __uint_as_float(r[q * 8 + 2 * t]) + f.y * __uint_as_float(r[q * 8 + 2 * t + 1]);
                     }
-                };
-                tmem_ld_32x32(tB + BT_TM_DP, ra);
+                }
+            }
+            const float ds128 = __bfloat162float(__float2bfloat16(p128 * (dp128 - delta) * p.scale));
+            dscol[i] = ds128;
+            mbar_wait(bar_dv, ph);                   // P is no longer read by the dV MMA: overwrite it with dS
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tB + BT_TM_DP + c * 32, r);
                 tmem_ld_wait();
-                tmem_ld_32x32(tB + BT_TM_DP + 32, rb);
-                ds_chunk(0, ra);
-                tmem_ld_wait();
-                tmem_ld_32x32(tB + BT_TM_DP + 64, ra);
-                ds_chunk(1, rb);
-                tmem_ld_wait();
-                tmem_ld_32x32(tB + BT_TM_DP + 96, rb);
-                ds_chunk(2, ra);
-                tmem_ld_wait();
-                ds_chunk(3, rb);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4* pa = reinterpret_cast<uint4*>(sP + (c >> 1) * BT_TILE + sw128(i, (c & 1) * 4 + q));
+                    uint4 u = *pa;
+                    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 f = __bfloat1622float2(hh[t]);
+                        hh[t] = __floats2bfloat162_rn(f.x * (__uint_as_float(r[q * 8 + 2 * t]) - delta) * p.scale,
+                                                      f.y * (__uint_as_float(r[q * 8 + 2 * t + 1]) - delta) * p.scale);
+                    }
+                    *pa = u;
+                }
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -810,7 +792,6 @@ int attention_tc_bwd(const EdbAttnDesc& d, cudaStream_t st) {
     AttnTcBwdParams p{};
     p.qkv = (const __nv_bfloat16*)d.qkv; p.ld_qkv = d.ld_qkv; p.d_qkv = (__nv_bfloat16*)d.d_qkv;
     p.P = (const __nv_bfloat16*)d.P;
-    p.out = (const __nv_bfloat16*)d.out; p.ld_out = d.ld_out;
     p.H = d.heads; p.scale = d.scale;
     p.idesc_dp = make_idesc_bf16(128, 128, 0, 0);
     p.idesc_kk_mn = make_idesc_bf16(128, AT_HD, 1, 1);

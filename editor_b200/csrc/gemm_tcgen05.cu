@@ -104,16 +104,80 @@ __device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& d) 
     d = fmaf(hx * fmaf(-th, th, 1.0f), q, fmaf(0.5f, th, 0.5f));
 }
 
+// Packed fp32 arithmetic (sm_100: fma/mul/add.rn.f32x2 -> FFMA2, one issue slot for two fp32 operations, full fp32
+// precision).  The GELU epilogues are ISSUE-bound (profiles/r01_ncu_gemm_fc1.txt: 123 M instructions, 57 % issue-active,
+// tensor pipe 52 %): the polynomial + derivative arithmetic of two neighbouring columns goes through one instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// same arithmetic, operation for operation, as gelu_fast / gelu_and_grad_fast on each half (fma.rn.f32x2 rounds each lane
+// like fma.rn.f32): the packed and the scalar epilogues produce bit-identical results
+__device__ __forceinline__ void gelu_pair_fast(float& x0, float& x1) {
+    const f32x2 x = pack2(x0, x1);
+    float t0, t1;
+    unpack2(mul2(x, x), t0, t1);
+    const f32x2 t = pack2(fminf(t0, 36.0f), fminf(t1, 36.0f));
+    const f32x2 cB = pack2(kGeluB, kGeluB), cA = pack2(kGeluA, kGeluA), cC = pack2(kGeluC, kGeluC);
+    float u0, u1;
+    unpack2(mul2(x, fma2(fma2(cC, t, cB), t, cA)), u0, u1);
+    const f32x2 th = pack2(tanh_approx(u0), tanh_approx(u1));
+    const f32x2 hx = mul2(pack2(0.5f, 0.5f), x);
+    unpack2(fma2(hx, th, hx), x0, x1);
+}
+__device__ __forceinline__ void gelu_and_grad_pair_fast(float& x0, float& x1, float& d0, float& d1) {
+    const f32x2 x = pack2(x0, x1);
+    float t0, t1;
+    unpack2(mul2(x, x), t0, t1);
+    const f32x2 t = pack2(fminf(t0, 36.0f), fminf(t1, 36.0f));
+    const f32x2 cB = pack2(kGeluB, kGeluB), cA = pack2(kGeluA, kGeluA), cC = pack2(kGeluC, kGeluC);
+    float u0, u1;
+    unpack2(mul2(x, fma2(fma2(cC, t, cB), t, cA)), u0, u1);
+    const float th0 = tanh_approx(u0), th1 = tanh_approx(u1);
+    const f32x2 th = pack2(th0, th1), nth = pack2(-th0, -th1);
+    const f32x2 q = fma2(fma2(pack2(5.0f * kGeluC, 5.0f * kGeluC), t, pack2(3.0f * kGeluB, 3.0f * kGeluB)), t, cA);
+    const f32x2 half = pack2(0.5f, 0.5f), one = pack2(1.0f, 1.0f);
+    const f32x2 hx = mul2(half, x);
+    unpack2(fma2(hx, th, hx), x0, x1);
+    unpack2(fma2(mul2(hx, fma2(nth, th, one)), q, fma2(half, th, half)), d0, d1);
+}
+#ifndef EDB_GELU_PACKED
+#define EDB_GELU_PACKED 1
+#endif
 __device__ __forceinline__ float4 gelu4_fast(float4 v) {
+#if EDB_GELU_PACKED
+    gelu_pair_fast(v.x, v.y);
+    gelu_pair_fast(v.z, v.w);
+    return v;
+#else
     return make_float4(gelu_fast(v.x), gelu_fast(v.y), gelu_fast(v.z), gelu_fast(v.w));
+#endif
 }
 // v <- gelu(v), returns gelu'(v)
 __device__ __forceinline__ float4 gelu4_and_grad_fast(float4& v) {
     float4 d;
+#if EDB_GELU_PACKED
+    gelu_and_grad_pair_fast(v.x, v.y, d.x, d.y);
+    gelu_and_grad_pair_fast(v.z, v.w, d.z, d.w);
+#else
     gelu_and_grad_fast(v.x, v.x, d.x);
     gelu_and_grad_fast(v.y, v.y, d.y);
     gelu_and_grad_fast(v.z, v.z, d.z);
     gelu_and_grad_fast(v.w, v.w, d.w);
+#endif
     return d;
 }
 // v * (saved bf16 gelu' factor)

@@ -102,6 +102,9 @@ SIGNATURES = {
     "edb_eval_normalize": (c_int, [c_vp, c_ll, c_int, c_int, c_float, c_vp]),
     "edb_eval_distmat": (c_int, [c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_vp]),
     "edb_eval_rank": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "edb_augment_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+    "edb_augment_u8": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int,
+                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None
@@ -147,20 +150,19 @@ gemm_timing = None  # bench.py sets this to a list to collect one record (shape,
 
 
 _capture_debug = os.environ.get("EDB_CAPTURE_DEBUG")       # tools/graph_probe.py: report the call that invalidates a capture
-_capture_was_active = False
+capture_window = False          # set by tools/graph_probe.py around `with torch.cuda.graph(...)`
 
 
 def call(name, *args):
-    global launch_count, _capture_was_active
+    global launch_count
     launch_count += 1
     check(getattr(load(), name)(*args))
-    if _capture_debug:
+    if _capture_debug and capture_window:
+        import threading
         active = torch.cuda.is_current_stream_capturing()
-        if _capture_was_active and not active:
-            import traceback
-            print("EDB_CAPTURE_DEBUG: capture no longer active after %s (launch %d)" % (name, launch_count), flush=True)
-            traceback.print_stack(limit=8)
-        _capture_was_active = active
+        if not active:
+            print("EDB_CAPTURE_DEBUG: %s launched on a NON-capturing stream %#x inside the capture window (thread %s)" % (
+                name, torch.cuda.current_stream().cuda_stream, threading.current_thread().name), flush=True)
 
 
 def gemm_set_mode(mode):

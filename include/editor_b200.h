@@ -144,8 +144,7 @@ int edb_gelu_bwd_f32(const float* dh, const float* pre, float* out, size_t n, vo
  * Also serves AttentionMask (vit_pytorch.py:240-258) on packed kept tokens. */
 typedef struct EdbAttnDesc {
     const void* qkv; long long ld_qkv;
-    void* out; long long ld_out;            /* forward: O.  backward: the SAME forward output, read-only -- required by the
-                                               tensor-core 129-token path (delta_i = dO_i . O_i), ignored by the others */
+    void* out; long long ld_out;            /* forward: O.  backward: unused (may be NULL) */
     void* P; long long p_rows; long long ldp;
     const int* seq_off; int fixed_len; int nseq; int heads; int max_len;
     float scale;
@@ -248,6 +247,30 @@ int edb_eval_distmat(const float* qf, long long ldq, int q, const float* gf, lon
  * queries with more than 2048 correct matches (not evaluated).  CMC[r] = mean_q [first_rank <= r+1], mAP = mean_q ap. */
 int edb_eval_rank(const float* dist, long long ldd, int q, int g, const long long* q_pid, const long long* g_pid,
                   const long long* q_key, const long long* g_key, double* ap, int* first_rank, int* overflow, void* stream);
+
+/* ---- training-time input pipeline (the step before the path, data/datasets/make_dataloader.py) -------- */
+
+/* Per-image random draws of the augmentation, made on the host (editor_b200/data.py): RandomHorizontalFlip,
+ * RandomCrop offsets inside the padded image (0 .. 2*PADDING), RandomErasing rectangle (e_h == 0: no erasing) and the
+ * Philox key of its noise. */
+typedef struct EdbAugImage {
+    int flip, top, left;
+    int e_top, e_left, e_h, e_w;
+    unsigned seed_lo, seed_hi;
+} EdbAugImage;
+
+/* T.Resize(SIZE_TRAIN, interpolation=3) -> RandomHorizontalFlip -> Pad(PADDING) -> RandomCrop(SIZE_TRAIN) -> ToTensor ->
+ * Normalize(mean, std) -> RandomErasing(mode='pixel', max_count=1)  (make_dataloader.py:245-253; RandomErasing :55-140)
+ * for the 3 x B modality images of a batch (bases.py:100-103).  src_*: uint8 [B][Hs][Ws][3] (decoded images of ONE size);
+ * out_*: fp32 [B][3][H][W].  hb/hk (vb/vk): bounds [W][2] ([H][2]) and 22-bit fixed-point coefficients [W][ksh] ([H][ksv]) of
+ * Pillow's bicubic resample for Ws -> W (Hs -> H), needed only for an axis that is resized.  params: [3*B] device array,
+ * image m*B + b.  noise: optional fp32 [3*B][3][H][W] normal draws used inside the erase rectangles (tests inject
+ * torch's); NULL -> Philox4x32-10 + Box-Muller keyed by params[].seed_*.  mean/std: host pointers to 3 floats. */
+size_t edb_augment_workspace_bytes(int B, int Hs, int Ws, int W);
+int edb_augment_u8(const unsigned char* src_rgb, const unsigned char* src_ni, const unsigned char* src_ti, int B, int Hs,
+                   int Ws, int H, int W, int pad, const int* hb, const int* hk, int ksh, const int* vb, const int* vk,
+                   int ksv, const float* mean, const float* std, const EdbAugImage* params, const float* noise,
+                   float* out_rgb, float* out_ni, float* out_ti, void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,8 +46,14 @@ def stage(name):
     mode = {"full_step_threadlocal": "thread_local", "full_step_relaxed": "relaxed"}.get(name, "global")
     g = torch.cuda.CUDAGraph()
     n0 = lib.launch_count
-    with torch.cuda.graph(g, capture_error_mode=mode):
-        out = body()
+    lib.capture_window = True
+    print("capture stream will be a side stream; default stream is %#x" % torch.cuda.default_stream().cuda_stream, flush=True)
+    try:
+        with torch.cuda.graph(g, capture_error_mode=mode):
+            print("capturing on %#x" % torch.cuda.current_stream().cuda_stream, flush=True)
+            out = body()
+    finally:
+        lib.capture_window = False
     n1 = lib.launch_count
     for _ in range(3):
         g.replay()
@@ -62,11 +68,9 @@ if __name__ == "__main__":
         for s in STAGES:
             r = subprocess.run([sys.executable, __file__, s], capture_output=True, text=True, timeout=600,
                                env=dict(os.environ, EDB_CAPTURE_DEBUG="1"))
-            dbg = [l for l in r.stdout.splitlines() if "EDB_CAPTURE_DEBUG" in l]
-            if dbg:
-                print("   ", dbg[0], flush=True)
-                print("\n".join(r.stderr.splitlines()[:12]) if False else "", end="")
-                idx = r.stderr.find("File")
-                print("   stack:", " | ".join(l.strip() for l in r.stderr.splitlines()[:16] if l.strip())[:1200], flush=True)
+            dbg = [l for l in r.stdout.splitlines() if "EDB_CAPTURE_DEBUG" in l or "captur" in l]
+            for l in dbg[:12]:
+                print("   ", l, flush=True)
+            print("    (%d debug lines)" % len(dbg), flush=True)
             ok = [l for l in r.stdout.splitlines() if l.startswith("STAGE")]
             print(ok[0] if ok else "STAGE %s FAILED: %s" % (s, " | ".join(r.stderr.strip().splitlines()[-6:])[:1500]), flush=True)
