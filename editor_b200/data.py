@@ -80,6 +80,8 @@ class GpuAugment:
         self.mean = (ctypes.c_float * 3)(*[float(v) for v in cfg.INPUT.PIXEL_MEAN])
         self.std = (ctypes.c_float * 3)(*[float(v) for v in cfg.INPUT.PIXEL_STD])
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.rng = np.random.default_rng(seed)
         self._tables = {}
         self._ws = None

@@ -849,7 +849,11 @@ class _HMAFn(torch.autograd.Function):
         eng._mark("hma_fwd_start")
         cls_out, patch_mean, cls_mid, loss_bcc, num, sv = eng.hma_forward(tokens, eng.sel, prec, True)
         eng._mark("hma_fwd_end")
-        eng.last = dict(num=num, tokens=tokens)
+        # detached: a graph-attached tensor kept here would keep the whole previous step's autograd graph -- and with it the
+        # AccumulateGrad node of every parameter, bound to the stream it was created on -- alive into the next step; under
+        # CUDA-graph capture the engine then syncs the capture stream with that foreign "leaf stream"
+        # (cudaErrorStreamCaptureIsolation)
+        eng.last = dict(num=num, tokens=tokens.detach())
         ctx.eng, ctx.sv, ctx.sel, ctx.nparams, ctx.prec = eng, sv, eng.sel, len(params), prec
         ctx.save_for_backward(tokens)
         return cls_out, patch_mean, cls_mid, loss_bcc

@@ -151,6 +151,22 @@ gemm_timing = None  # bench.py sets this to a list to collect one record (shape,
 
 _capture_debug = os.environ.get("EDB_CAPTURE_DEBUG")       # tools/graph_probe.py: report the call that invalidates a capture
 capture_window = False          # set by tools/graph_probe.py around `with torch.cuda.graph(...)`
+_cudart = None
+
+
+def capture_status(stream=None):
+    """cudaStreamIsCapturing of the current stream: 0 = none, 1 = active, 2 = invalidated (debugging aid)."""
+    global _cudart
+    if _cudart is None:
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _cudart = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+    st = ctypes.c_int(-1)
+    rc = _cudart.cudaStreamIsCapturing(ctypes.c_void_p(stream if stream is not None else stream_ptr()), ctypes.byref(st))
+    return st.value if rc == 0 else -rc
 
 
 def call(name, *args):
@@ -158,11 +174,16 @@ def call(name, *args):
     launch_count += 1
     check(getattr(load(), name)(*args))
     if _capture_debug and capture_window:
-        import threading
-        active = torch.cuda.is_current_stream_capturing()
-        if not active:
-            print("EDB_CAPTURE_DEBUG: %s launched on a NON-capturing stream %#x inside the capture window (thread %s)" % (
-                name, torch.cuda.current_stream().cuda_stream, threading.current_thread().name), flush=True)
+        st = capture_status()
+        if st != 1:
+            import threading
+            import traceback
+            print("EDB_CAPTURE_DEBUG: after %s (launch %d, thread %s) the capture status of stream %#x is %d "
+                  "(0 none, 1 active, 2 invalidated)" % (name, launch_count, threading.current_thread().name,
+                                                         torch.cuda.current_stream().cuda_stream, st), flush=True)
+            if not getattr(call, "_reported", False):
+                call._reported = True
+                print("".join(traceback.format_stack(limit=10)), flush=True)
 
 
 def gemm_set_mode(mode):

@@ -104,11 +104,18 @@ class Trainer:
                 self.step(*self.static_in)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        # no autograd graph of an earlier step may survive into the capture: the AccumulateGrad nodes of the parameters are
+        # cached while any graph references them and carry the stream they were created on; the autograd engine would
+        # sync the capture stream with that uncaptured stream (cudaErrorStreamCaptureIsolation)
+        import gc
+        gc.collect()
         n0 = lib.launch_count
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.static_loss, self.static_out = self.step(*self.static_in)
+                loss, outs = self.step(*self.static_in)
+                self.static_loss, self.static_out = loss.detach(), tuple(o.detach() for o in outs)
+                del loss, outs
         except Exception as e:          # noqa: BLE001 - any capture failure leaves the trainer in eager mode
             self.graph, self.capture_error = None, repr(e)[:300]
             torch.cuda.synchronize()

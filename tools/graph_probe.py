@@ -6,7 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-STAGES = ["fwd_loss", "fwd_loss_bwd", "full_step"]
+STAGES = ["fwd_loss_bwd", "full_step"]
 
 
 def stage(name):
@@ -51,7 +51,28 @@ def stage(name):
     try:
         with torch.cuda.graph(g, capture_error_mode=mode):
             print("capturing on %#x" % torch.cuda.current_stream().cuda_stream, flush=True)
-            out = body()
+            cap = torch.cuda.current_stream().cuda_stream
+            # a torch-level watcher between python statements: first line after which the capture is no longer active
+            import sys as _sys
+            state = {"bad": False}
+
+            def tracer(frame, event, arg):
+                if event == "line" and not state["bad"] and ("editor_b200" in frame.f_code.co_filename or "graph_probe" in frame.f_code.co_filename):
+                    st = lib.capture_status(cap)
+                    if st != 1:
+                        state["bad"] = True
+                        print("EDB_CAPTURE_DEBUG: status %d first seen BEFORE executing %s:%d (%s)" % (
+                            st, frame.f_code.co_filename, frame.f_lineno, frame.f_code.co_name), flush=True)
+                return tracer
+            import threading as _th
+            _th.settrace(tracer)
+            _sys.settrace(tracer)
+            try:
+                out = body()
+            finally:
+                _sys.settrace(None)
+                _th.settrace(None)
+            print("EDB_CAPTURE_DEBUG: status at the end of the body: %d" % lib.capture_status(cap), flush=True)
     finally:
         lib.capture_window = False
     n1 = lib.launch_count
@@ -68,9 +89,12 @@ if __name__ == "__main__":
         for s in STAGES:
             r = subprocess.run([sys.executable, __file__, s], capture_output=True, text=True, timeout=600,
                                env=dict(os.environ, EDB_CAPTURE_DEBUG="1"))
-            dbg = [l for l in r.stdout.splitlines() if "EDB_CAPTURE_DEBUG" in l or "captur" in l]
-            for l in dbg[:12]:
+            dbg = [l for l in r.stdout.splitlines() if "EDB_CAPTURE_DEBUG" in l or "captur" in l or "File" in l or l.startswith("    ")]
+            for l in dbg[:40]:
                 print("   ", l, flush=True)
             print("    (%d debug lines)" % len(dbg), flush=True)
             ok = [l for l in r.stdout.splitlines() if l.startswith("STAGE")]
+            if not ok:
+                print("---- full stderr of stage %s ----" % s, flush=True)
+                print(r.stderr[-6000:], flush=True)
             print(ok[0] if ok else "STAGE %s FAILED: %s" % (s, " | ".join(r.stderr.strip().splitlines()[-6:])[:1500]), flush=True)
