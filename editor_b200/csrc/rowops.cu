@@ -118,8 +118,15 @@ ln_bwd_kernel(const DyT* __restrict__ dy, long long lddy, const float* __restric
         const float sc = row_scale ? row_scale[row / scale_group] : 1.0f;
         const float* xr = x + (size_t)row * ldx;
         const DyT* dr = dy + (size_t)row * lddy;
-        float4 xh[VPL], d[VPL];
+        float4 xh[VPL], d[VPL], gi[VPL];
         float s1 = 0.f, s2 = 0.f;
+        // the incoming residual gradient is requested together with x and dy: 18 instead of 12 independent 16-byte loads
+        // in flight per lane (the kernel runs one 8-warp CTA per SM and is bound by bytes in flight: 0.74 of the HBM
+        // copy bandwidth in profiles/r01_ncu_sfts_ln.txt with the g_in loads issued after the row reduction)
+        if (g_in) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) gi[j] = load4(g_in + (size_t)row * ldg + (j * 32 + lane) * 4);
+        }
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int c = (j * 32 + lane) * 4;
@@ -139,10 +146,7 @@ ln_bwd_kernel(const DyT* __restrict__ dy, long long lddy, const float* __restric
             const int c = (j * 32 + lane) * 4;
             float4 o = make_float4(rs * (d[j].x - c1 - xh[j].x * c2), rs * (d[j].y - c1 - xh[j].y * c2),
                                    rs * (d[j].z - c1 - xh[j].z * c2), rs * (d[j].w - c1 - xh[j].w * c2));
-            if (g_in) {
-                const float4 gi = load4(g_in + (size_t)row * ldg + c);
-                o.x += gi.x; o.y += gi.y; o.z += gi.z; o.w += gi.w;
-            }
+            if (g_in) { o.x += gi[j].x; o.y += gi[j].y; o.z += gi[j].z; o.w += gi[j].w; }
             if (g_out) store4(g_out + (size_t)row * ldg + c, o.x, o.y, o.z, o.w);
             if (g_bf16) store4(g_bf16 + (size_t)row * ldgb + c, sc * o.x, sc * o.y, sc * o.z, sc * o.w);
             acc_c[j].x += sc * o.x; acc_c[j].y += sc * o.y; acc_c[j].z += sc * o.z; acc_c[j].w += sc * o.w;
