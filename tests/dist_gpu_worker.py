@@ -68,6 +68,22 @@ def main():
     opt = torch.optim.SGD(groups, momentum=0.9)
     m3, _, _, _, _ = fresh()
     tr3 = Trainer(m3)
+    def agreement():
+        p2, p3 = dict(m2.named_parameters()), dict(m3.named_parameters())
+        num = den = 0.0
+        per = []
+        for k in p2:
+            if p2[k].grad is None:
+                continue
+            upd = (p3[k].detach().cpu() - sd[k]).double().norm().item()
+            diff = (p2[k].detach() - p3[k].detach()).double().norm().item()
+            num, den = num + diff ** 2, den + upd ** 2
+            if upd > 1e-12:
+                per.append(diff / upd)
+        per.sort()
+        return {"whole_model": (num / max(den, 1e-300)) ** 0.5, "per_tensor_median": per[len(per) // 2], "per_tensor_max": per[-1]}
+
+    report["ddp_vs_trainer_param_err_rel_update"] = []
     for _ in range(2):
         opt.zero_grad()
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -75,21 +91,8 @@ def main():
         l2.backward()
         opt.step()
         l3, _ = tr3.step(x, label, cam)
-    torch.cuda.synchronize()
-    p2, p3 = dict(m2.named_parameters()), dict(m3.named_parameters())
-    num = den = 0.0
-    per = []
-    for k in p2:
-        if p2[k].grad is None:
-            continue
-        upd = (p3[k].detach().cpu() - sd[k]).double().norm().item()
-        diff = (p2[k].detach() - p3[k].detach()).double().norm().item()
-        num, den = num + diff ** 2, den + upd ** 2
-        if upd > 1e-12:
-            per.append(diff / upd)
-    per.sort()
-    report["ddp_vs_trainer_param_err_rel_update"] = {"whole_model": (num / max(den, 1e-300)) ** 0.5,
-                                                     "per_tensor_median": per[len(per) // 2], "per_tensor_max": per[-1]}
+        torch.cuda.synchronize()
+        report["ddp_vs_trainer_param_err_rel_update"].append(agreement())
     report["ddp_loss"], report["trainer_loss"] = l2.item(), l3.item()
     a, b = m2.state_dict()["FUSE_BN.running_mean"], m3.state_dict()["FUSE_BN.running_mean"]
     report["bn_running_mean_err"] = ((a - b).abs().max() / b.abs().max()).item()

@@ -14,7 +14,7 @@ def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     dev = torch.device("cuda", 0)
     from editor_b200.train import Trainer
-    model, sd, x, label, cam = bench.build_case(dev, 128, seed=1)
+    model, sd, x, label, cam, _ = bench.build_case(dev, 128, seed=1)
     model.train()
     tr = Trainer(model)
     xg = {k: v.to(dev) for k, v in x.items()}

@@ -100,8 +100,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     summarize_launches()
     g = summarize_rep("prof_gemm")
-    for n in ("prof_attn_fwd", "prof_attn_bwd", "prof_sfts_ln", "prof_gemm_fc1", "prof_gemm_fc2d", "prof_gemm_proj",
-              "prof_gemm_fc1d"):
+    for n in ("prof_attn_fwd", "prof_attn_bwd", "prof_sfts", "prof_ln", "prof_augment", "prof_gemm_fc1", "prof_gemm_fc2d",
+              "prof_gemm_proj", "prof_gemm_fc1d"):
         summarize_rep(n)
     if g:
         tr = []
@@ -111,8 +111,8 @@ def main():
             tr.append(rd + wr)
         json.dump({"kernel": "gemm_bf16_kernel", "captured_launches": len(tr), "dram_bytes_per_launch": tr,
                    "mean_dram_bytes_per_launch": sum(tr) / len(tr)}, open(os.path.join(OUT, "%s_gemm_traffic.json" % TAG), "w"), indent=1)
-    for f in ("bench_own.json", "bench_ref.json", "sfts_bench.json", "pytest_gpu.log", "gemm_bench.txt", "attn_bench.txt",
-              "step_trace.txt"):
+    for f in ("bench_own.json", "bench_ref.json", "bench_rgbnt100.json", "bench_msvr310_fp32.json", "pytest_gpu.log",
+              "gemm_bench.txt", "attn_bench.txt", "ln_bench.txt", "step_trace.txt"):
         src = os.path.join(ROOT, "gpurun_out", f)
         if os.path.exists(src):
             open(os.path.join(OUT, "%s_%s" % (TAG, f)), "w").write(open(src).read())
