@@ -572,8 +572,7 @@ def main():
             eval_metrics["cpu_sample"] = "oracle/eval_oracle.py on %d of the %d queries" % (ns, nq)
         del fd
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     ms_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
@@ -638,8 +637,26 @@ def main():
         except (KeyError, TypeError, ZeroDivisionError):
             pass
     print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Leave without tearing NCCL down.  At 8 ranks `dist.destroy_process_group()` never returned once the step had been
+    captured into a CUDA graph (the communicator is still referenced by the graph's captured collectives; seen on an
+    8 x B200 box: the JSON line was out after 60 s, the processes sat in the teardown until the launcher's timeout).  Every
+    rank waits for the others (so no rank exits under a peer's collective), flushes, and exits the process directly:
+    the driver and the OS reclaim the communicator, the graph and the device memory."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:      # noqa: BLE001 - nothing left to do but exit
+            pass
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -107,9 +107,14 @@ class R1_mAP_eval:
         self.pids.extend(np.asarray(pid))
         self.camids.extend(np.asarray(camid))
 
+    def _normalizes(self):
+        """utils/metrics.py:263 tests `if self.feat_norm:` -- ANY non-empty string (also TEST.FEAT_NORM 'no') normalises;
+        R1_mAP (:217) compares with 'yes'.  Mirrored as written."""
+        return bool(self.feat_norm)
+
     def _split(self):
         feats = torch.cat(self.feats, dim=0)
-        if self.feat_norm in (True, "yes"):
+        if self._normalizes():
             print("The test feature is normalized")
             feats = normalize_(feats.clone())
         return feats[:self.num_query], feats[self.num_query:]
@@ -129,6 +134,9 @@ class R1_mAP(R1_mAP_eval):
 
     def __init__(self, num_query, max_rank=50, feat_norm="yes"):
         super().__init__(num_query, max_rank, feat_norm)
+
+    def _normalizes(self):
+        return self.feat_norm == "yes"                 # utils/metrics.py:217
 
     def reset(self):
         super().reset()
