@@ -292,8 +292,7 @@ def reference_gpu_legs(args):
     eager = {"what": "UNMODIFIED reference model + make_loss + make_optimizer trained by engine/processor.py::do_train on "
                      "this GPU, B=%d, synthetic P x K batches from pinned host memory" % args.batch,
              "fp16_scaler": leg("--model", "reference", "--amp", "fp16"),
-             "bf16": leg("--model", "reference", "--amp", "bf16"),
-             "bf16_device_resident_inputs": leg("--model", "reference", "--amp", "bf16", "--resident")}
+             "bf16": leg("--model", "reference", "--amp", "bf16")}
     dropin = {"what": "this repo's make_model driven by the same unmodified do_train (GradScaler + per-tensor torch SGD)",
               "fp16_scaler": leg("--model", "ours", "--amp", "fp16")}
     return eager, dropin
@@ -630,10 +629,11 @@ def main():
             line["vs_torch_eager_gpu"] = {
                 "e2e_over_reference_bf16": e2e_v / ref_bf16,
                 "e2e_over_reference_fp16_scaler": e2e_v / eager["fp16_scaler"]["images_per_sec"],
-                "value_over_reference_bf16_resident": value / eager["bf16_device_resident_inputs"]["images_per_sec"],
+                "value_over_reference_bf16": value / ref_bf16,
                 "dropin_do_train_over_reference_fp16_scaler": dropin["fp16_scaler"]["images_per_sec"]
                 / eager["fp16_scaler"]["images_per_sec"],
-                "note": "same GPU, same process lifetime, same B and yml; reference legs are single-GPU"}
+                "note": "same GPU, same B and yml; the reference legs read their batches from pinned host memory inside the "
+                        "iteration (measured in round 2: 1.5 % of its 185 ms; device-resident inputs 697 vs 688 img/s)"}
         except (KeyError, TypeError, ZeroDivisionError):
             pass
     print(json.dumps(line), flush=True)

@@ -239,6 +239,10 @@ class EditorEngine:
         if self.arena is not None and self.arena.device == device and self.arena.intact():
             return
         m = self.model
+        frozen = [n for n, p in m.named_parameters() if not p.requires_grad and ".memory_cls." not in n]
+        if frozen:      # the arena holds the trainable parameters only; OCFR's centre banks are the reference's own frozen ones
+            raise lib.EdbError("parameters with requires_grad=False are not supported by the flat parameter arena "
+                               "(%s ...): keep them trainable and give them lr 0 / exclude them from the optimizer" % frozen[0])
         self.arena = Arena(m, device)
         self.ws = Workspace(device)
         base = "BACKBONE.base."
@@ -258,6 +262,14 @@ class EditorEngine:
         self.hma_names = [n for n in self.arena.names if n.startswith("FUSE_block.")]
         self.bb_plist = [self.arena.params[self.arena.names.index(n)] for n in self.bb_names]
         self.hma_plist = [self.arena.params[self.arena.names.index(n)] for n in self.hma_names]
+
+    def mark_params_dirty(self):
+        """Call after changing parameters in a way torch's version counters do not see (`p.data.mul_()`, EMA, clipping
+        through `.data`, a custom optimizer writing raw storage): the bf16 shadow and the fp32 split caches are refreshed
+        when `p._version` or the arena generation changes, and `.data` updates bump neither."""
+        if self.arena is not None:
+            self.arena.generation += 1
+            self.arena.refresh16(force=True)
 
     def _mark(self, name):
         ev = self.stats.get("events")
