@@ -649,6 +649,10 @@ def finish(world):
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
+        # belt and braces: the line is already out; if even the closing barrier should stall, leave after a minute
+        t = threading.Timer(60.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         try:
             torch.cuda.synchronize()
             dist.barrier()

@@ -117,3 +117,50 @@ def test_trainer_flags_and_gradient_buckets():
     # the model still owns its parameters after the arena re-binds their storage
     sd = model.state_dict()
     assert sd["BACKBONE.base.pos_embed"].data_ptr() == arena.view("BACKBONE.base.pos_embed").data_ptr()
+
+
+def test_arena_grad_contract_accumulates_like_torch():
+    """engine.Arena.prepare_grads / finish_grads (host logic, CPU tensors): `.grad` views of the flat arena accumulate over
+    backward passes until the caller zeroes them; a foreign `.grad` is adopted once; parameters without a `.grad` carry
+    nothing.  (The kernels of one backward WRITE most gradients, so each backward starts from a zeroed arena.)"""
+    import __graft_entry__ as ge
+    from editor_b200.engine import Arena
+    model, *_ = ge._small_case(False, 2)
+    arena = Arena(model, torch.device("cpu"))
+    names = ["BACKBONE.base.blocks.3.attn.qkv.bias", "FUSE_BN.weight", "BACKBONE_HEAD.weight"]
+    params = dict(model.named_parameters())
+
+    def fake_backward(value):
+        """what a step's kernels do: overwrite / fill their slices of the (zeroed) arena, then expose them"""
+        for n in names:
+            arena.gview(n).fill_(value)
+        arena.attach_grads(set(names))
+        arena.finish_grads()
+
+    # 1. zero_grad(set_to_none=True): every .grad None -> one memset, plain gradients
+    arena.grad.fill_(7.0)
+    arena.prepare_grads()
+    assert float(arena.grad.abs().max()) == 0.0 and not arena.carry_live
+    fake_backward(1.0)
+    assert all(torch.all(params[n].grad == 1.0) for n in names)
+    assert params[names[0]].grad.data_ptr() == arena.gview(names[0]).data_ptr()
+    # 2. second backward without zeroing: old + new
+    arena.prepare_grads()
+    assert arena.carry_live and float(arena.grad.abs().max()) == 0.0
+    fake_backward(2.0)
+    assert all(torch.all(params[n].grad == 3.0) for n in names)
+    # 3. zero_grad(set_to_none=False) zeroes the views in place -> the next backward starts over
+    for n in names:
+        params[n].grad.zero_()
+    arena.prepare_grads()
+    fake_backward(5.0)
+    assert all(torch.all(params[n].grad == 5.0) for n in names)
+    # 4. a foreign .grad tensor is adopted once and re-pointed at the arena; a parameter whose .grad is None carries nothing
+    params[names[1]].grad = None
+    params[names[2]].grad = torch.full_like(params[names[2]], 10.0)
+    arena.prepare_grads()
+    fake_backward(1.0)
+    assert torch.all(params[names[0]].grad == 6.0)          # 5 carried + 1
+    assert torch.all(params[names[1]].grad == 1.0)          # nothing carried
+    assert torch.all(params[names[2]].grad == 11.0)         # foreign 10 adopted + 1
+    assert params[names[2]].grad.data_ptr() == arena.gview(names[2]).data_ptr()
