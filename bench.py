@@ -367,10 +367,20 @@ def main():
 
     # ---- device-resident throughput ("value")
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # the whole step (forward + loss + backward + allreduce + SGD) as one CUDA graph: Trainer.capture; eager otherwise
     graphed = (not args.no_graph) and (not fp32) and trainer.capture(xg, lg, cg)
+    if world > 1:       # every rank replays, or none does
+        flag = torch.tensor([1 if graphed else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        graphed = bool(flag.item()) and graphed
+    if not graphed and not args.no_graph and not fp32 and world == 1:
+        # a failed capture leaves torch's CUDA generator in capture mode (the next torch.rand raises): start over eagerly
+        sys.stderr.write("bench.py: CUDA-graph capture failed (%s); restarting with --no-graph\n"
+                         % getattr(trainer, "capture_error", None))
+        sys.stderr.flush()
+        os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+    if rank == 0:
+        sampler.start()                      # (after the capture: a restart above must not orphan the nvidia-smi child)
     if graphed:
         xg, lg, cg = trainer.static_in       # device-resident inputs = the graph's static buffers (no per-step D2D copy)
     step_fn = trainer.step_graphed if graphed else trainer.step
