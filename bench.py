@@ -596,7 +596,9 @@ def main():
                        "l2_policy": "inputs+activations per step (>18 GB) far exceed the 126 MB L2",
                        "kept_tokens_mean": n_sel, "drop_path": drop_path, "preheat_steps": args.preheat,
                        "step": "forward + CE/triplet loss + backward + grad allreduce + fused SGD",
-                       "cuda_graph": bool(graphed), "cuda_graph_error": getattr(trainer, "capture_error", None)},
+                       "cuda_graph": bool(graphed), "cuda_graph_error": getattr(trainer, "capture_error", None),
+                       "untimed_steps_before_warmup": {"graph_capture_warmup": 3 if graphed else 0,
+                                                       "preheat": args.preheat}},
             "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
