@@ -30,5 +30,5 @@ def test_two_rank_allreduce_and_ddp_equal_trainer(al):
     # second step: two bf16 trainings whose weights differ in the last bits (measured 6e-3)
     assert step1["whole_model"] < 2e-4 and step1["per_tensor_median"] < 1e-3, rep
     assert step2["whole_model"] < 1e-2 and step2["per_tensor_median"] < 1e-2, rep
-    assert abs(rep["ddp_loss"] - rep["trainer_loss"]) < 2e-3 * abs(rep["trainer_loss"])
+    assert abs(rep["ddp_loss"] - rep["trainer_loss"]) < 1e-2 * abs(rep["trainer_loss"])      # loss of the 2nd step
     assert rep["bn_running_mean_err"] < 5e-3
