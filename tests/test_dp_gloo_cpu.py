@@ -164,3 +164,45 @@ def test_arena_grad_contract_accumulates_like_torch():
     assert torch.all(params[names[1]].grad == 1.0)          # nothing carried
     assert torch.all(params[names[2]].grad == 11.0)         # foreign 10 adopted + 1
     assert params[names[2]].grad.data_ptr() == arena.gview(names[2]).data_ptr()
+
+
+def _trainer_bucket_worker(rank, world, port, out):
+    """The REAL train.Trainer bucket code (Trainer._setup + Trainer._on_grad_stage) on a CPU arena over gloo: the stages
+    are reported in the order the engine's backward reports them; afterwards every element of the gradient arena must
+    hold the sum over ranks -- covered exactly once, no hole, no double reduction."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as ge
+    from editor_b200.engine import Arena, GRAD_STAGE_BLOCKS
+    from editor_b200.train import Trainer
+    model, *_ = ge._small_case(False, 2)
+    arena = Arena(model, torch.device("cpu"))
+    eng = model.engine()
+    eng.arena = arena                                    # (the engine would build it on the first CUDA forward)
+    tr = Trainer(model)
+    assert tr.world == world
+    tr._setup(arena)
+    g = torch.Generator().manual_seed(1000 + rank)
+    arena.grad.copy_(torch.randn(arena.total, generator=g))
+    local = arena.grad.clone()
+    # engine.backbone_backward: "after_backbone" first, then the block stages in descending order, then "rest"
+    for stage in ["after_backbone"] + ["blocks_from_%d" % l for l in GRAD_STAGE_BLOCKS] + ["rest"]:
+        tr._on_grad_stage(stage)
+    assert len(tr.pending) == 2 + len(GRAD_STAGE_BLOCKS)
+    for w in tr.pending:
+        w.wait()
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    want = sum(gathered)
+    if rank == 0:
+        torch.save({"max_err": float((arena.grad - want).abs().max()), "total": arena.total}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_buckets_allreduce_every_element_once(tmp_path):
+    out = str(tmp_path / "buckets.pt")
+    mp.spawn(_trainer_bucket_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got["total"] > 100_000_000 and got["max_err"] == 0.0        # fp32 sums of two ranks: exact, whatever the bucket
